@@ -1,0 +1,493 @@
+// C ABI of the pbx library (include/pbx.h): plan management, launch orchestration, reductions.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pbx_fast.cuh"
+#include "pbx_generic.cuh"
+
+using namespace pbx;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(PBX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define PBX_NEED_DEVICE(p) do { if ((p)->device < 0) return fail(PBX_ERR_CUDA, "host-only plan (device -1): nothing can be launched, pbx has no CPU fallback"); } while (0)
+#define PBX_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+constexpr size_t kScratchTarget = (size_t)1 << 30;  // aim for <= 1 GiB of intermediates per chunk
+constexpr long long kFastCoordChunk = 1 << 16;      // samples per transposed-coordinate chunk
+
+// ---- per-block sums ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pbx_block_sums_kernel(const double* __restrict__ out4, long long ld, long long n_samples, long long block_size,
+                      double delta_beta, int pm, double* __restrict__ sums) {
+    __shared__ double sh[PBX_NSUMS][256];
+    const long long blk = blockIdx.x;
+    const long long lo = blk * block_size, hi = min(lo + block_size, n_samples);
+    double acc[PBX_NSUMS];
+#pragma unroll
+    for (int k = 0; k < PBX_NSUMS; ++k) acc[k] = 0.0;
+    const double inv2db = pm ? 1.0 / (2.0 * delta_beta) : 0.0, invdb2 = pm ? 1.0 / (delta_beta * delta_beta) : 0.0;
+    for (long long x = lo + threadIdx.x; x < hi; x += 256) {
+        const double rho = out4[x], g = out4[ld + x];
+        const double r = g / rho;
+        acc[0] += r; acc[3] = fma(r, r, acc[3]);
+        if (pm) {
+            const double gp = out4[2 * ld + x], gm = out4[3 * ld + x];
+            const double rp = gp / rho, rm = gm / rho;
+            const double d1 = (gp - gm) / rho * inv2db, d2 = (gp - 2.0 * g + gm) / rho * invdb2;
+            acc[1] += rp; acc[2] += rm; acc[4] += d1; acc[5] += d2;
+            acc[6] = fma(d1, d1, acc[6]); acc[7] = fma(d2, d2, acc[7]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PBX_NSUMS; ++k) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+#pragma unroll
+            for (int k = 0; k < PBX_NSUMS; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < PBX_NSUMS) sums[blk * PBX_NSUMS + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// ---- FP64 peak probe: 8 independent dependent-FMA chains per thread ------------------------------
+__global__ void __launch_bounds__(256) pbx_dfma_probe_kernel(double* out, int iters, double a, double b) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = threadIdx.x * 1e-9 + k;
+    for (int i = 0; i < iters; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 123.456) out[0] = s;  // never true; keeps the loop alive
+}
+
+}  // namespace
+
+struct pbx_plan {
+    HostTables H;
+    int device = 0;
+    uint32_t flags = 0;
+    bool pm = false, jacobi = false, scale = true;
+    double* dev_tables = nullptr;
+    DevTables D{};
+    const FastKernelEntry* fast = nullptr;
+    std::vector<unsigned char> fast_tables;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* io = nullptr;  // device staging for the *_host entry points
+    size_t io_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    long long launches = 0;
+};
+
+namespace {
+
+int ensure(void** buf, size_t* have, size_t need) {
+    if (need <= *have) return PBX_OK;
+    if (*buf) { PBX_CUDA(cudaDeviceSynchronize()); PBX_CUDA(cudaFree(*buf)); *buf = nullptr; *have = 0; }
+    PBX_CUDA(cudaMalloc(buf, need));
+    *have = need;
+    return PBX_OK;
+}
+
+int upload_tables(pbx_plan* p) {
+    const HostTables& H = p->H;
+    std::vector<double> flat;
+    auto push = [&](const std::vector<double>& v) { size_t off = flat.size(); flat.insert(flat.end(), v.begin(), v.end()); return off; };
+    std::vector<double> hc(H.coth.size()), cs(H.csch);
+    for (size_t i = 0; i < hc.size(); ++i) hc[i] = -0.5 * H.coth[i];
+    const size_t o_dv = push(H.d_vib), o_dr = push(H.d_rho), o_hc = push(hc), o_cs = push(cs), o_lp = push(H.logpref),
+                 o_lpr = push(H.logpref_rho), o_wc = push(H.wcum), o_e = push(H.e_off), o_l = push(H.l_off),
+                 o_q = push(H.q_pack), o_s = push(H.samp);
+    PBX_CUDA(cudaMalloc((void**)&p->dev_tables, flat.size() * sizeof(double)));
+    PBX_CUDA(cudaMemcpy(p->dev_tables, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+    DevTables& D = p->D;
+    D.A = H.A; D.Ar = H.Ar; D.N = H.N; D.P = H.P; D.AA = H.AA; D.NN = H.NN; D.n_rho_eval = H.n_rho_eval;
+    D.neg_tau = -H.tau[0];
+    const double* b = p->dev_tables;
+    D.d_vib = b + o_dv; D.d_rho = b + o_dr; D.hc = b + o_hc; D.cs = b + o_cs; D.lpref = b + o_lp;
+    D.lpref_rho = b + o_lpr; D.wcum = b + o_wc; D.e_off = b + o_e; D.l_off = b + o_l; D.q_pack = b + o_q;
+    D.samp = b + o_s;
+    return PBX_OK;
+}
+
+// doubles of intermediates per sample on the generic path (coords excluded)
+size_t generic_doubles_per_sample(const HostTables& H) {
+    return (size_t)H.P * ((size_t)H.A * H.A + 3 * (size_t)H.A + H.Ar);
+}
+
+int launch_generic(pbx_plan* p, const double* R, long long n, double* out4, long long out_ld, cudaStream_t st) {
+    // R: [n][N][P] device; intermediates in p->scratch (caller sized it)
+    const HostTables& H = p->H;
+    double* m_mat = (double*)p->scratch;
+    double* o_vib = m_mat + (size_t)n * H.P * H.A * H.A;
+    double* lr = o_vib + (size_t)3 * n * H.P * H.A;
+    BeadOutputs bo{};
+    bo.o_vib = o_vib; bo.lr = lr; bo.m_mat = m_mat; bo.n = n;
+    const long long items = n * H.P;
+    const unsigned grid_b = (unsigned)((items + GEN_WARPS - 1) / GEN_WARPS);
+    const size_t sm_b = GEN_WARPS * bead_warp_doubles(H.A, H.Ar, H.N) * sizeof(double);
+    auto kb = p->jacobi ? (p->scale ? pbx_bead_kernel<true, true> : pbx_bead_kernel<true, false>)
+                        : (p->scale ? pbx_bead_kernel<false, true> : pbx_bead_kernel<false, false>);
+    PBX_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+    kb<<<grid_b, GEN_WARPS * 32, sm_b, st>>>(p->D, R, n, bo);
+    PBX_CUDA(cudaGetLastError());
+    const unsigned grid_c = (unsigned)((n + GEN_WARPS - 1) / GEN_WARPS);
+    const size_t sm_c = GEN_WARPS * chain_warp_doubles(H.A, H.Ar) * sizeof(double);
+    if (p->pm) {
+        PBX_CUDA(cudaFuncSetAttribute(pbx_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        pbx_chain_kernel<true><<<grid_c, GEN_WARPS * 32, sm_c, st>>>(p->D, m_mat, o_vib, lr, n, out4, out4 + out_ld, out_ld);
+    } else {
+        PBX_CUDA(cudaFuncSetAttribute(pbx_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        pbx_chain_kernel<false><<<grid_c, GEN_WARPS * 32, sm_c, st>>>(p->D, m_mat, o_vib, lr, n, out4, out4 + out_ld, out_ld);
+    }
+    PBX_CUDA(cudaGetLastError());
+    p->launches += 2;
+    return PBX_OK;
+}
+
+int launch_sample_coords(pbx_plan* p, unsigned long long seed, long long first, long long n, double* R, int* src,
+                         cudaStream_t st) {
+    const int threads = 64;
+    const size_t sm = (size_t)2 * p->H.N * threads * sizeof(double);
+    PBX_CUDA(cudaFuncSetAttribute(pbx_sample_coords_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    pbx_sample_coords_kernel<<<(unsigned)((n + threads - 1) / threads), threads, sm, st>>>(p->D, seed, first, n, R, src);
+    PBX_CUDA(cudaGetLastError());
+    p->launches += 1;
+    return PBX_OK;
+}
+
+long long generic_chunk(const pbx_plan* p, long long n, bool with_coords) {
+    size_t per = generic_doubles_per_sample(p->H) + (with_coords ? (size_t)p->H.N * p->H.P : 0);
+    long long c = (long long)(kScratchTarget / (per * sizeof(double)));
+    c = std::max<long long>(c, 1);
+    return std::min(c, n);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pbx_abi_version(void) { return PBX_ABI_VERSION; }
+const char* pbx_last_error(void) { return g_last_error.c_str(); }
+
+int pbx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pbx_plan_create(const pbx_model* vib, const pbx_rho* rho, int32_t beads, double beta, double delta_beta,
+                    uint32_t flags, int32_t device, pbx_plan** out) {
+    if (!out) return fail(PBX_ERR_ARG, "out is null");
+    *out = nullptr;
+    pbx_plan* p = new (std::nothrow) pbx_plan();
+    if (!p) return fail(PBX_ERR_ARG, "out of host memory");
+    std::string err;
+    int rc = build_tables(vib, rho, beads, beta, delta_beta, flags, p->H, err);
+    if (rc != PBX_OK) { delete p; return fail(rc, err); }
+    p->device = device; p->flags = flags;
+    p->pm = flags & PBX_FLAG_PM; p->jacobi = flags & PBX_FLAG_EIG_JACOBI; p->scale = !(flags & PBX_FLAG_NO_SCALING);
+    const bool want_fast = !(flags & PBX_FLAG_FORCE_GENERIC) && p->scale;
+    if (want_fast) p->fast = find_fast_kernel(p->H.A, p->H.N, p->H.Ar);
+    if (p->fast) {
+        p->fast_tables.assign(p->fast->table_bytes, 0);
+        p->fast->fill(p->H, p->fast_tables.data());
+    }
+    if (device == -1) {  // host-only plan: tables can be inspected (pbx_plan_table), nothing can be launched
+        *out = p;
+        return PBX_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        delete p;
+        cudaGetLastError();
+        return fail(PBX_ERR_CUDA, "no CUDA device available: pbx has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) { delete p; return fail(PBX_ERR_ARG, "device index out of range"); }
+    DeviceGuard guard(device);
+    if (!guard.ok) { delete p; return fail(PBX_ERR_CUDA, "cudaSetDevice failed"); }
+    // shared-memory footprint of the generic kernels must fit an SM
+    const size_t sm_need = GEN_WARPS * std::max(bead_warp_doubles(p->H.A, p->H.Ar, p->H.N),
+                                                chain_warp_doubles(p->H.A, p->H.Ar)) * sizeof(double);
+    if (sm_need > 200 * 1024) { delete p; return fail(PBX_ERR_UNSUPPORTED, "A too large for the generic kernels"); }
+    rc = upload_tables(p);
+    if (rc != PBX_OK) { pbx_plan_destroy(p); return rc; }
+    e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { pbx_plan_destroy(p); return cuda_fail(e, "cudaStreamCreate"); }
+    *out = p;
+    return PBX_OK;
+}
+
+int pbx_plan_destroy(pbx_plan* p) {
+    if (!p) return PBX_OK;
+    if (p->device < 0) { delete p; return PBX_OK; }
+    DeviceGuard guard(p->device);
+    cudaDeviceSynchronize();
+    if (p->dev_tables) cudaFree(p->dev_tables);
+    if (p->scratch) cudaFree(p->scratch);
+    if (p->io) cudaFree(p->io);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+    return PBX_OK;
+}
+
+int64_t pbx_plan_table(const pbx_plan* p, const char* name, double* out, int64_t count) {
+    if (!p || !name) return fail(PBX_ERR_ARG, "null argument");
+    const HostTables& H = p->H;
+    const std::vector<double>* v = nullptr;
+    std::vector<double> tmp;
+    const std::string s(name);
+    if (s == "d_vib") v = &H.d_vib; else if (s == "d_rho") v = &H.d_rho;
+    else if (s == "delta_vib") v = &H.delta_vib; else if (s == "delta_rho") v = &H.delta_rho;
+    else if (s == "weights") v = &H.weights; else if (s == "coth") v = &H.coth; else if (s == "csch") v = &H.csch;
+    else if (s == "logpref") v = &H.logpref; else if (s == "logpref_rho") v = &H.logpref_rho;
+    else if (s == "e_off") v = &H.e_off; else if (s == "l_off") v = &H.l_off; else if (s == "q_pack") v = &H.q_pack;
+    else if (s == "samp") v = &H.samp;
+    else if (s == "tau") { tmp.assign(H.tau, H.tau + 3); v = &tmp; }
+    else return fail(PBX_ERR_ARG, "unknown table name: " + s);
+    const int64_t avail = (int64_t)v->size();
+    if (out && count > 0) std::memcpy(out, v->data(), (size_t)std::min(count, avail) * sizeof(double));
+    return avail;
+}
+
+int pbx_plan_is_fast(const pbx_plan* p) { return (p && p->fast) ? 1 : 0; }
+int64_t pbx_plan_launch_count(const pbx_plan* p) { return p ? p->launches : 0; }
+
+int pbx_sample_eval_dev(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n, double* out4, void* stream) {
+    if (!p || !out4) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0) return PBX_OK;
+    if (first_sample < 0) return fail(PBX_ERR_ARG, "first_sample < 0");
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->fast) {
+        FastLaunch L{};
+        L.samp = p->D.samp; L.seed = seed; L.first_sample = first_sample; L.n_samples = n; L.out4 = out4; L.out_ld = n;
+        PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_SAMPLE, p->pm, p->jacobi, st));
+        p->launches += 1;
+        return PBX_OK;
+    }
+    const long long chunk = generic_chunk(p, n, true);
+    const size_t per = generic_doubles_per_sample(p->H), coords = (size_t)p->H.N * p->H.P;
+    int rc = ensure(&p->scratch, &p->scratch_bytes, (size_t)chunk * (per + coords) * sizeof(double));
+    if (rc != PBX_OK) return rc;
+    double* R = (double*)p->scratch + (size_t)chunk * per;
+    for (long long off = 0; off < n; off += chunk) {
+        const long long m = std::min<long long>(chunk, n - off);
+        rc = launch_sample_coords(p, seed, first_sample + off, m, R, nullptr, st);
+        if (rc != PBX_OK) return rc;
+        rc = launch_generic(p, R, m, out4 + off, n, st);
+        if (rc != PBX_OK) return rc;
+    }
+    return PBX_OK;
+}
+
+int pbx_eval_coords_dev(pbx_plan* p, const double* R, int64_t n, double* out4, void* stream) {
+    if (!p || !R || !out4) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0) return PBX_OK;
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const HostTables& H = p->H;
+    if (p->fast) {
+        const long long chunk = std::min<long long>(kFastCoordChunk, n);
+        const long long ld = (chunk + 31) / 32 * 32, np = (long long)H.N * H.P;
+        int rc = ensure(&p->scratch, &p->scratch_bytes, (size_t)ld * np * sizeof(double));
+        if (rc != PBX_OK) return rc;
+        for (long long off = 0; off < n; off += chunk) {
+            const long long m = std::min<long long>(chunk, n - off);
+            dim3 grid((unsigned)((np + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
+            pbx_transpose_kernel<<<grid, block, 0, st>>>(R + (size_t)off * np, (double*)p->scratch, m, np, ld);
+            PBX_CUDA(cudaGetLastError());
+            FastLaunch L{};
+            L.samp = p->D.samp; L.coords_t = (const double*)p->scratch; L.ld = ld; L.n_samples = m;
+            L.out4 = out4 + off; L.out_ld = n;
+            PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_COORDS, p->pm, p->jacobi, st));
+            p->launches += 2;
+        }
+        return PBX_OK;
+    }
+    const long long chunk = generic_chunk(p, n, false);
+    int rc = ensure(&p->scratch, &p->scratch_bytes, (size_t)chunk * generic_doubles_per_sample(H) * sizeof(double));
+    if (rc != PBX_OK) return rc;
+    for (long long off = 0; off < n; off += chunk) {
+        const long long m = std::min<long long>(chunk, n - off);
+        rc = launch_generic(p, R + (size_t)off * H.N * H.P, m, out4 + off, n, st);
+        if (rc != PBX_OK) return rc;
+    }
+    return PBX_OK;
+}
+
+int pbx_sample_coords_dev(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n, double* R, int32_t* src,
+                          void* stream) {
+    if (!p || !R) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0) return PBX_OK;
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    return launch_sample_coords(p, seed, first_sample, n, R, src, (cudaStream_t)stream);
+}
+
+int pbx_eval_stages_dev(pbx_plan* p, const double* R, int64_t n, double* o_rho, double* o_vib, double* scale,
+                        double* v_mat, double* m_mat, void* stream) {
+    if (!p || !R) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0) return PBX_OK;
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const HostTables& H = p->H;
+    BeadOutputs bo{};
+    bo.o_rho = o_rho; bo.o_vib = o_vib; bo.scale = scale; bo.v_mat = v_mat; bo.m_mat = m_mat; bo.n = n;
+    const long long items = n * H.P;
+    const size_t sm_b = GEN_WARPS * bead_warp_doubles(H.A, H.Ar, H.N) * sizeof(double);
+    auto kb = p->jacobi ? (p->scale ? pbx_bead_kernel<true, true> : pbx_bead_kernel<true, false>)
+                        : (p->scale ? pbx_bead_kernel<false, true> : pbx_bead_kernel<false, false>);
+    PBX_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+    kb<<<(unsigned)((items + GEN_WARPS - 1) / GEN_WARPS), GEN_WARPS * 32, sm_b, st>>>(p->D, R, n, bo);
+    PBX_CUDA(cudaGetLastError());
+    p->launches += 1;
+    return PBX_OK;
+}
+
+int pbx_chain_trace_dev(pbx_plan* p, const double* m_mat, const double* o_diag, int64_t n, double* g_out,
+                        void* stream) {
+    if (!p || !m_mat || !o_diag || !g_out) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0) return PBX_OK;
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    const size_t sm_c = GEN_WARPS * chain_warp_doubles(p->H.A, p->H.Ar) * sizeof(double);
+    PBX_CUDA(cudaFuncSetAttribute(pbx_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+    pbx_chain_kernel<false><<<(unsigned)((n + GEN_WARPS - 1) / GEN_WARPS), GEN_WARPS * 32, sm_c, (cudaStream_t)stream>>>(
+        p->D, m_mat, o_diag, nullptr, n, nullptr, g_out, n);
+    PBX_CUDA(cudaGetLastError());
+    p->launches += 1;
+    return PBX_OK;
+}
+
+int pbx_block_sums_dev(pbx_plan* p, const double* out4, int64_t n, int64_t block_size, double* sums, void* stream) {
+    if (!p || !out4 || !sums) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0 || block_size <= 0) return fail(PBX_ERR_ARG, "n_samples and block_size must be positive");
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    const long long blocks = (n + block_size - 1) / block_size;
+    pbx_block_sums_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out4, n, n, block_size, p->H.delta_beta,
+                                                                             p->pm ? 1 : 0, sums);
+    PBX_CUDA(cudaGetLastError());
+    p->launches += 1;
+    return PBX_OK;
+}
+
+int pbx_sample_eval_host(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n, double* out4_host,
+                         int64_t ld_host, int64_t block_size, double* sums_host) {
+    if (!p || !out4_host) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0) return PBX_OK;
+    if (ld_host < n) return fail(PBX_ERR_ARG, "ld_host < n_samples");
+    if (sums_host && block_size <= 0) return fail(PBX_ERR_ARG, "block_size must be positive");
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    const int64_t blocks = sums_host ? (n + block_size - 1) / block_size : 0;
+    int rc = ensure(&p->io, &p->io_bytes, ((size_t)4 * n + (size_t)blocks * PBX_NSUMS) * sizeof(double));
+    if (rc != PBX_OK) return rc;
+    double* out_dev = (double*)p->io;
+    double* sums_dev = out_dev + (size_t)4 * n;
+    rc = pbx_sample_eval_dev(p, seed, first_sample, n, out_dev, p->own_stream);
+    if (rc != PBX_OK) return rc;
+    if (sums_host) {
+        rc = pbx_block_sums_dev(p, out_dev, n, block_size, sums_dev, p->own_stream);
+        if (rc != PBX_OK) return rc;
+    }
+    const size_t rows = p->pm ? 4 : 2;
+    PBX_CUDA(cudaMemcpy2DAsync(out4_host, ld_host * sizeof(double), out_dev, n * sizeof(double), n * sizeof(double), rows,
+                               cudaMemcpyDeviceToHost, p->own_stream));
+    if (sums_host)
+        PBX_CUDA(cudaMemcpyAsync(sums_host, sums_dev, (size_t)blocks * PBX_NSUMS * sizeof(double), cudaMemcpyDeviceToHost,
+                                 p->own_stream));
+    PBX_CUDA(cudaStreamSynchronize(p->own_stream));
+    return PBX_OK;
+}
+
+int pbx_eval_coords_host(pbx_plan* p, const double* R_host, int64_t n, double* out4_host, int64_t ld_host) {
+    if (!p || !R_host || !out4_host) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0) return PBX_OK;
+    if (ld_host < n) return fail(PBX_ERR_ARG, "ld_host < n_samples");
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    const size_t np = (size_t)p->H.N * p->H.P;
+    const size_t out_bytes = (size_t)4 * n * sizeof(double);
+    int rc = ensure(&p->io, &p->io_bytes, out_bytes + n * np * sizeof(double));
+    if (rc != PBX_OK) return rc;
+    double* out_dev = (double*)p->io;
+    double* R_dev = out_dev + (size_t)4 * n;
+    PBX_CUDA(cudaMemcpyAsync(R_dev, R_host, n * np * sizeof(double), cudaMemcpyHostToDevice, p->own_stream));
+    rc = pbx_eval_coords_dev(p, R_dev, n, out_dev, p->own_stream);
+    if (rc != PBX_OK) return rc;
+    const size_t rows = p->pm ? 4 : 2;
+    PBX_CUDA(cudaMemcpy2DAsync(out4_host, ld_host * sizeof(double), out_dev, n * sizeof(double), n * sizeof(double), rows,
+                               cudaMemcpyDeviceToHost, p->own_stream));
+    PBX_CUDA(cudaStreamSynchronize(p->own_stream));
+    return PBX_OK;
+}
+
+int pbx_fp64_peak_tflops(int32_t device, double* tflops_out) {
+    if (!tflops_out) return fail(PBX_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(PBX_ERR_CUDA, "no such CUDA device");
+    }
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    PBX_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* dummy = nullptr;
+    PBX_CUDA(cudaMalloc((void**)&dummy, 8));
+    const int grid = prop.multiProcessorCount * 8, iters = 1 << 15;
+    cudaEvent_t e0, e1;
+    PBX_CUDA(cudaEventCreate(&e0)); PBX_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        PBX_CUDA(cudaEventRecord(e0));
+        pbx_dfma_probe_kernel<<<grid, 256>>>(dummy, iters, 0.999999, 1e-7);
+        PBX_CUDA(cudaEventRecord(e1));
+        PBX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        PBX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * iters * 256.0 * grid;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dummy);
+    *tflops_out = best;
+    return PBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// Device building blocks shared by all pbx kernels: Philox4x32-10, FP64 Box-Muller, and the two
+// ways of forming M = exp(-tau V) for a small symmetric V held in registers
+// (reference: np.linalg.eigh + einsum, /root/reference/pibronic/pimc/pimc.py:1171-1187).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pbx_tables.hpp"
+
+namespace pbx {
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (sample_lo, sample_hi, draw, stream), key = seed
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0; k.y += W1;
+    }
+    return c;
+}
+
+enum : uint32_t { STREAM_NORMALS = 0u, STREAM_SOURCE = 1u };
+
+// 64 random bits -> double in (0, 1]
+__device__ __forceinline__ double u01_open_low(uint32_t hi, uint32_t lo) {
+    const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+    return ((double)(bits >> 11) + 1.0) * 0x1.0p-53;
+}
+// 64 random bits -> double in [0, 1)
+__device__ __forceinline__ double u01_half_open(uint32_t hi, uint32_t lo) {
+    const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+    return (double)(bits >> 11) * 0x1.0p-53;
+}
+
+// two independent N(0,1) variates from one Philox block (Box-Muller, all FP64)
+__device__ __forceinline__ void normal_pair(uint4 r, double& z0, double& z1) {
+    const double u1 = u01_open_low(r.x, r.y);
+    const double u2 = u01_half_open(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+}
+
+// mixture component: first a with u < wcum[a]
+template <int AR, typename WC>
+__device__ __forceinline__ int pick_source(double u, const WC& wcum) {
+    int src = 0;
+#pragma unroll
+    for (int a = 0; a < AR - 1; ++a) src += (u >= wcum[a]) ? 1 : 0;
+    return src;
+}
+
+// ------------------------------------------------------------------------------------------
+// small symmetric matrices in registers, packed lower triangle (index tri(i,j), i >= j)
+// ------------------------------------------------------------------------------------------
+template <int A> struct SymMat { double v[A * (A + 1) / 2]; };
+
+// C = X*Y for COMMUTING symmetric X, Y (so C is symmetric): A*(A+1)/2 * A FMAs
+template <int A>
+__device__ __forceinline__ void sym_mul(const double (&X)[A * (A + 1) / 2], const double (&Y)[A * (A + 1) / 2],
+                                        double (&C)[A * (A + 1) / 2]) {
+#pragma unroll
+    for (int i = 0; i < A; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double acc = X[sym(i, 0)] * Y[sym(0, j)];
+#pragma unroll
+            for (int k = 1; k < A; ++k) acc = fma(X[sym(i, k)], Y[sym(k, j)], acc);
+            C[tri(i, j)] = acc;
+        }
+}
+
+// M = exp(X) for symmetric X by scaling and squaring with a degree-12 Taylor polynomial evaluated
+// Paterson-Stockmeyer style (X^2, X^3, X^4 + two Horner steps in X^4 = 5 products) and
+// s = max(0, ceil(log2(||X||_1 / 0.25))) squarings.  Truncation error <= 0.25^13/13! = 2.4e-18.
+template <int A>
+__device__ __forceinline__ void sym_expm(double (&X)[A * (A + 1) / 2], double (&M)[A * (A + 1) / 2]) {
+    constexpr int AA = A * (A + 1) / 2;
+    double norm = 0.0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+        double row = 0.0;
+#pragma unroll
+        for (int j = 0; j < A; ++j) row += fabs(X[sym(i, j)]);
+        norm = fmax(norm, row);
+    }
+    // norm = m * 2^e with m in [0.5, 1): scaling by 2^-(e+2) brings the norm below 0.25
+    int s = ((__double2hiint(norm) >> 20) & 0x7ff) - 1022 + 2;
+    s = s < 0 ? 0 : (s > 60 ? 60 : s);
+    const double scale = __hiloint2double((1023 - s) << 20, 0);
+#pragma unroll
+    for (int k = 0; k < AA; ++k) X[k] *= scale;
+    double X2[AA], X3[AA], X4[AA], B[AA], Cm[AA];
+    sym_mul<A>(X, X, X2);
+    sym_mul<A>(X, X2, X3);
+    sym_mul<A>(X2, X2, X4);
+    constexpr double c2 = 1.0 / 2, c3 = 1.0 / 6, c4 = 1.0 / 24, c5 = 1.0 / 120, c6 = 1.0 / 720, c7 = 1.0 / 5040,
+                     c8 = 1.0 / 40320, c9 = 1.0 / 362880, c10 = 1.0 / 3628800, c11 = 1.0 / 39916800,
+                     c12 = 1.0 / 479001600;
+    // B2 = c8 I + c9 X + c10 X2 + c11 X3 + c12 X4
+#pragma unroll
+    for (int k = 0; k < AA; ++k) B[k] = fma(c12, X4[k], fma(c11, X3[k], fma(c10, X2[k], c9 * X[k])));
+#pragma unroll
+    for (int i = 0; i < A; ++i) B[tri(i, i)] += c8;
+    sym_mul<A>(X4, B, Cm);
+    // B1 + X4*B2
+#pragma unroll
+    for (int k = 0; k < AA; ++k) B[k] = Cm[k] + fma(c7, X3[k], fma(c6, X2[k], c5 * X[k]));
+#pragma unroll
+    for (int i = 0; i < A; ++i) B[tri(i, i)] += c4;
+    sym_mul<A>(X4, B, Cm);
+#pragma unroll
+    for (int k = 0; k < AA; ++k) M[k] = Cm[k] + fma(c3, X3[k], fma(c2, X2[k], X[k]));
+#pragma unroll
+    for (int i = 0; i < A; ++i) M[tri(i, i)] += 1.0;
+    for (int q = 0; q < s; ++q) {
+        sym_mul<A>(M, M, Cm);
+#pragma unroll
+        for (int k = 0; k < AA; ++k) M[k] = Cm[k];
+    }
+}
+
+// M = U exp(lambda) U^T with (lambda, U) from a cyclic Jacobi eigensolve of symmetric X, all in
+// registers (indices are compile-time constants after unrolling).  Sweeps run until the
+// off-diagonal mass is below 1e-33 * ||X||_F^2 for every lane of the warp (max 12 sweeps).
+template <int A>
+__device__ __forceinline__ void sym_exp_jacobi(const double (&X)[A * (A + 1) / 2], double (&M)[A * (A + 1) / 2]) {
+    double S[A][A], U[A][A];
+#pragma unroll
+    for (int i = 0; i < A; ++i)
+#pragma unroll
+        for (int j = 0; j < A; ++j) { S[i][j] = X[sym(i, j)]; U[i][j] = (i == j) ? 1.0 : 0.0; }
+    double fro = 0.0;
+#pragma unroll
+    for (int i = 0; i < A; ++i)
+#pragma unroll
+        for (int j = 0; j < A; ++j) fro = fma(S[i][j], S[i][j], fro);
+    const double tol = 1e-33 * fro;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int i = 1; i < A; ++i)
+#pragma unroll
+            for (int j = 0; j < i; ++j) off = fma(S[i][j], S[i][j], off);
+        if (__all_sync(__activemask(), off <= tol)) break;
+#pragma unroll
+        for (int p = 0; p < A - 1; ++p)
+#pragma unroll
+            for (int q = p + 1; q < A; ++q) {
+                const double apq = S[p][q];
+                double c = 1.0, sn = 0.0;
+                if (fabs(apq) > 1e-300) {
+                    const double theta = (S[q][q] - S[p][p]) / (2.0 * apq);
+                    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                    c = rsqrt(fma(t, t, 1.0));
+                    sn = t * c;
+                    S[p][p] = fma(-t, apq, S[p][p]);
+                    S[q][q] = fma(t, apq, S[q][q]);
+                    S[p][q] = 0.0; S[q][p] = 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    if (k != p && k != q) {
+                        const double akp = S[k][p], akq = S[k][q];
+                        const double np_ = fma(c, akp, -sn * akq), nq_ = fma(sn, akp, c * akq);
+                        S[k][p] = np_; S[p][k] = np_;
+                        S[k][q] = nq_; S[q][k] = nq_;
+                    }
+                    const double ukp = U[k][p], ukq = U[k][q];
+                    U[k][p] = fma(c, ukp, -sn * ukq);
+                    U[k][q] = fma(sn, ukp, c * ukq);
+                }
+            }
+    }
+    double ev[A];
+#pragma unroll
+    for (int k = 0; k < A; ++k) ev[k] = exp(S[k][k]);
+#pragma unroll
+    for (int i = 0; i < A; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < A; ++k) acc = fma(U[i][k] * ev[k], U[j][k], acc);
+            M[tri(i, j)] = acc;
+        }
+}
+
+}  // namespace pbx
