@@ -209,6 +209,8 @@ class Plan:
         if out4 is None:
             out4 = np.full((4, n), np.nan)
         assert out4.dtype == np.float64 and out4.ndim == 2 and out4.shape[0] in (2, 4) and out4.shape[1] >= n
+        if out4.shape[1] == 0:
+            return out4, max(n, 1)
         assert out4.strides[1] == 8 and out4.strides[0] % 8 == 0, "rows must be contiguous float64"
         return out4, out4.strides[0] // 8
 

@@ -29,7 +29,9 @@ class FileStructure:
             setattr(self, f"path_vib_{_SHORT[sub]}", join(self.path_data, sub + "/"))
         self._point_at_rho(id_rho)
         self.template_sos_vib = self.path_vib_params + "sos_B{B:d}.json"
-        self.dir_list = [a for a in dir(self) if a.startswith('path_')]
+        # attribute names of the DIRECTORIES (the path_* attributes naming files are not in this list)
+        self.dir_list = ['path_root', 'path_data', 'path_es', 'path_rho'] + \
+            [f'path_{kind}_{_SHORT[sub]}' for kind in ('vib', 'rho') for sub in _SUB_DIRS]
 
         self.path_vib_model = join(self.path_vib_params, file_name.coupled_model)
         self.path_har_model = join(self.path_vib_params, file_name.harmonic_model)

@@ -35,3 +35,366 @@ def test_eval_coords_matches_reference(cuda, case, variant):
     for k in (1, 2, 3):
         assert rel_err(out[k] / out[0], want[k] / want[0]) < RTOL
     plan.close()
+
+
+# ------------------------------------------------------------------ helpers
+def oracle_eval(tab, R, pm=True):
+    from oracle import pimc_oracle as orc
+    return np.stack(orc.estimate_block(tab, R, pm=pm, faithful=False))
+
+
+def drawn_coords(cuda, plan, seed, first, n):
+    with cuda.cuda.device(plan.device):
+        R = cuda.empty((n, plan.N, plan.P), dtype=cuda.float64, device="cuda")
+        src = cuda.empty(n, dtype=cuda.int32, device="cuda")
+        plan.sample_coords(seed, first, n, R, src)
+        return R.cpu().numpy(), src.cpu().numpy()
+
+
+# ------------------------------------------------------------------ reference KAT, step by step
+def test_stage_kernels_reproduce_the_references_known_answers(cuda, tmp_path):
+    """the reference's tests/pimc/test_pimc_explicit_example.py::test_block_compute, run against this
+    package's step helpers (CUDA stage kernels): rho_oMat, vib_oMat, vib_mMat, rho, g"""
+    from os.path import join
+    from conftest import GOLDEN
+    from pibronic_b200 import file_structure, pimc
+    from pibronic_b200.pimc import build_o_matrix, build_denominator, diagonalize_coupling_matrix, build_numerator
+    kat = np.load(join(GOLDEN, "explicit_kat.npz"))
+    FS = file_structure.FileStructure(tmp_path, id_data=0, id_rho=0)
+    for name, path in (("coupled_model", FS.path_vib_model), ("sampling_model", FS.path_rho_model)):
+        with open(path, "w", encoding="UTF8") as fh:
+            fh.write(str(kat[name + "_json"]))
+    data = pimc.BoxData.from_FileStructure(FS)
+    data.samples, data.beads, data.temperature, data.block_size = 10, 5, 300.00, 2
+    data.blocks = data.samples // data.block_size
+    data.preprocess()
+    results = pimc.BoxResult(data=data)
+    results.path_root, results.id_job = FS.path_rho_results, 0
+    rho, vib = data.rho, data.vib
+    y_rho, y_g = results.scaled_rho.view(), results.scaled_g.view()
+    RTOL_, ATOL_ = 1e-05, 1e-08
+    for block_index in range(data.blocks):
+        view = slice(block_index * data.block_size, (block_index + 1) * data.block_size)
+        data.qTensor = kat["samples"][view, ...]
+        build_o_matrix(data, rho.const, rho.state_shift)
+        assert np.allclose(rho.const.omatrix, kat["rho_oMat"][view, ...], rtol=RTOL_, atol=ATOL_)
+        build_o_matrix(data, vib.const, vib.state_shift)
+        assert np.allclose(vib.const.omatrix, kat["vib_oMat"][view, ...], rtol=RTOL_, atol=ATOL_)
+        build_denominator(rho.const, y_rho, view)
+        diagonalize_coupling_matrix(data)
+        build_numerator(data, vib.const, y_g, view)
+        assert np.allclose(data.M_matrix, kat["vib_mMat"][view, ...], rtol=RTOL_, atol=ATOL_)
+    assert np.allclose(y_rho, kat["denominator(rho)"], rtol=RTOL_, atol=ATOL_)
+    assert np.allclose(y_g, kat["numerator(g)"], rtol=RTOL_, atol=ATOL_)
+    # and far tighter than the reference's own tolerance
+    assert rel_err(y_g, kat["numerator(g)"]) < RTOL and rel_err(y_rho, kat["denominator(rho)"]) < RTOL
+    data.release()
+
+
+def test_stage_outputs_match_oracle(cuda, case):
+    """O factors (all four table sets), scale S, V and M for every bead against the oracle's intermediates"""
+    from oracle import pimc_oracle as orc
+    tab = case.oracle_tables(rho_trunc=True)
+    plan = case.plan()
+    details = {}
+    orc.estimate_block(tab, case.R, pm=True, faithful=False, details=details)
+    n, P, A, Ar = len(case.R), tab.P, tab.A, tab.Ar
+    t = cuda
+    with t.cuda.device(0):
+        R = t.from_numpy(case.R).cuda()
+        o_rho = t.empty((n, P, Ar), dtype=t.float64, device="cuda")
+        o_vib = t.empty((3, n, P, A), dtype=t.float64, device="cuda")
+        scale = t.empty((n, P), dtype=t.float64, device="cuda")
+        v_mat = t.empty((n, P, A, A), dtype=t.float64, device="cuda")
+        m_mat = t.empty((n, P, A, A), dtype=t.float64, device="cuda")
+        plan.eval_stages(R, o_rho=o_rho, o_vib=o_vib, scale=scale, v_mat=v_mat, m_mat=m_mat)
+        o_rho, o_vib, scale, v_mat, m_mat = (x.cpu().numpy() for x in (o_rho, o_vib, scale, v_mat, m_mat))
+    assert rel_err(scale, details["S"]) < 1e-11
+    keep = details["o_rho"] > 1e-280
+    assert np.max(np.abs(o_rho[keep] / details["o_rho"][keep] - 1)) < 1e-11
+    keep = details["o_vib"] > 1e-280
+    assert np.max(np.abs(o_vib[0][keep] / details["o_vib"][keep] - 1)) < 1e-11
+    vscale = np.abs(details["V"]).max() + 1e-300
+    assert np.max(np.abs(v_mat - details["V"])) < 1e-13 * vscale
+    mscale = np.abs(details["M"]).max(axis=(2, 3), keepdims=True)
+    assert np.max(np.abs(m_mat - details["M"]) / mscale) < 1e-12
+    plan.close()
+
+
+# ------------------------------------------------------------------ sampler
+def test_device_sampler_matches_its_cpu_restatement(cuda, case):
+    from oracle import philox_sampler as ps
+    tab = case.oracle_tables()
+    plan = case.plan()
+    samp = plan.table("samp").reshape(tab.P, tab.N, 3)
+    wcum = np.cumsum(plan.table("weights"))
+    n, seed, first = 257, 0xDEADBEEF12345678, (1 << 33) + 5      # 64-bit seed and counter
+    R, src = drawn_coords(cuda, plan, seed, first, n)
+    R_cpu, src_cpu = ps.sample_coords(samp, wcum, tab.d_rho, seed, first, n)
+    assert np.array_equal(src, src_cpu)
+    assert np.max(np.abs(R - R_cpu)) < 1e-11 * (1 + np.abs(R_cpu).max())
+    plan.close()
+
+
+@pytest.mark.parametrize("variant", ["default", "generic"])
+def test_fused_kernel_equals_sampler_then_estimator(cuda, case, variant):
+    """the fused sampler+estimator gives what the estimator gives on the coordinates the sampler kernel
+    reports for the same Philox counters -- and both match the oracle on those coordinates"""
+    flags = _cabi.FLAG_PM | _cabi.QUIRK_RHO_TRUNC | VARIANTS[variant]
+    plan = case.plan(flags)
+    tab = case.oracle_tables(rho_trunc=True)
+    n, seed, first = 300, 424242, 12345
+    fused = plan.sample_eval_host(seed, first, n)
+    R, _ = drawn_coords(cuda, plan, seed, first, n)
+    two_step = plan.eval_coords_host(R)
+    assert rel_err(fused, two_step) < 1e-12
+    want = oracle_eval(tab, R)
+    for k in range(4):
+        assert rel_err(fused[k], want[k]) < RTOL
+    plan.close()
+
+
+def test_results_do_not_depend_on_how_the_index_range_is_split(cuda, case):
+    plan = case.plan()
+    n, seed = 1000, 77
+    whole = plan.sample_eval_host(seed, 500, n)
+    parts = np.concatenate([plan.sample_eval_host(seed, 500, 333), plan.sample_eval_host(seed, 833, 667)], axis=1)
+    assert np.array_equal(whole, parts)
+    again = plan.sample_eval_host(seed, 500, n)
+    assert np.array_equal(whole, again)                                   # deterministic
+    other = plan.sample_eval_host(seed + 1, 500, n)
+    assert not np.array_equal(whole[1], other[1])
+    plan.close()
+
+
+# ------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("n", [1, 31, 129])
+def test_ragged_sample_counts(cuda, n):
+    from conftest import GoldenCase
+    case = GoldenCase("quad_3x4")
+    plan = case.plan()
+    tab = case.oracle_tables()
+    out = plan.sample_eval_host(5, 0, n)
+    R, _ = drawn_coords(cuda, plan, 5, 0, n)
+    want = oracle_eval(tab, R)
+    assert out.shape == (4, n) and rel_err(out, want) < RTOL
+    plan.close()
+
+
+def test_empty_input_is_a_no_op(cuda):
+    from conftest import GoldenCase
+    case = GoldenCase("c1_2x2")
+    plan = case.plan()
+    out = plan.sample_eval_host(5, 0, 0, out4=np.full((4, 0), np.nan))
+    assert out.shape == (4, 0)
+    plan.close()
+
+
+@pytest.mark.parametrize("P", [3, 4, 33])
+@pytest.mark.parametrize("variant", ["default", "generic"])
+def test_minimum_and_odd_bead_counts(cuda, P, variant):
+    from conftest import GoldenCase
+    from oracle import pimc_oracle as orc
+    case = GoldenCase("quad_3x4")
+    case.P = P
+    plan = case.plan(_cabi.FLAG_PM | VARIANTS[variant])
+    tab = orc.precompute(case.vib, case.rho, P, case.T)
+    n = 64
+    out = plan.sample_eval_host(9, 0, n)
+    R, _ = drawn_coords(cuda, plan, 9, 0, n)
+    assert rel_err(out, oracle_eval(tab, R)) < RTOL
+    plan.close()
+
+
+def test_non_pm_plan_fills_two_rows(cuda, case):
+    plan = case.plan(flags=_cabi.QUIRK_RHO_TRUNC)
+    out = np.full((2, len(case.R)), np.nan)
+    plan.eval_coords_host(case.R, out4=out)
+    assert rel_err(out, case.expected[:2]) < RTOL
+    plan.close()
+
+
+def test_sampling_model_with_fewer_surfaces_than_the_system(cuda):
+    """A_rho < A: the reference raises IndexError (pimc.py:1110-1111); mathematically it is fine"""
+    from conftest import GoldenCase
+    from oracle import pimc_oracle as orc
+    case = GoldenCase("quad_3x4")
+    case.rho = dict(A=2, N=case.rho["N"], E=case.rho["E"][:2].copy(), w=case.rho["w"], L=case.rho["L"][:, :2].copy())
+    plan = case.plan(_cabi.FLAG_PM)
+    assert not plan.is_fast
+    tab = orc.precompute(case.vib, case.rho, case.P, case.T)
+    out = plan.sample_eval_host(3, 0, 50)
+    R, src = drawn_coords(cuda, plan, 3, 0, 50)
+    assert set(src) <= {0, 1} and rel_err(out, oracle_eval(tab, R)) < RTOL
+    plan.close()
+
+
+def test_correct_rho_when_sampling_model_is_larger(cuda):
+    """default (no quirk flag): all A_rho surfaces enter rho(R) -- the mathematically correct estimator"""
+    from conftest import GoldenCase
+    case = GoldenCase("jt_rho4")
+    plan = case.plan(_cabi.FLAG_PM)
+    got = plan.eval_coords_host(case.R)
+    want = oracle_eval(case.oracle_tables(rho_trunc=False), case.R)
+    assert rel_err(got, want) < RTOL
+    assert np.any(np.abs(got[0] / case.expected[0] - 1) > 1e-3)      # differs from the reference's truncated rho
+    plan.close()
+
+
+# ------------------------------------------------------------------ block sums
+def test_block_sums_match_numpy(cuda, case):
+    from oracle import pimc_oracle as orc
+    plan = case.plan()
+    n, bs = 1000, 96                                                     # ragged last block
+    out, sums = plan.sample_eval_host(11, 0, n, block_size=bs)
+    ratio, d1, d2 = orc.property_terms(orc.DELTA_BETA, *out)
+    cols = (ratio, out[2] / out[0], out[3] / out[0], ratio ** 2, d1, d2, d1 ** 2, d2 ** 2)
+    assert sums.shape == (-(-n // bs), _cabi.NSUMS)
+    for b in range(sums.shape[0]):
+        sl = slice(b * bs, min((b + 1) * bs, n))
+        for k, col in enumerate(cols):
+            assert np.isclose(sums[b, k], col[sl].sum(), rtol=1e-11, atol=1e-11 * np.abs(col[sl]).sum())
+    plan.close()
+
+
+# ------------------------------------------------------------------ statistics on independent draws
+def test_estimators_agree_with_reference_sampler_within_error(cuda):
+    """Z, E, Cv from GPU draws vs the numpy port of the reference on its own (MT19937) draws"""
+    from conftest import GoldenCase
+    from oracle import pimc_oracle as orc
+    case = GoldenCase("quad_3x4")
+    tab = case.oracle_tables()
+    plan = case.plan()
+    Xg, Xc = 400000, 40000
+    gpu = plan.sample_eval_host(2024, 0, Xg)
+    cpu = orc.run_blocks(tab, Xc, 10000, np.random.RandomState(99), pm=True, faithful=False)
+
+    def blocks(out, nb=40):
+        """Z, E, Cv per block of samples: their spread is the (jackknife-like) error estimate"""
+        vals = []
+        for part in np.array_split(np.arange(out.shape[1]), nb):
+            r, d1, d2 = orc.property_terms(orc.DELTA_BETA, *out[:, part])
+            p = orc.basic_properties(len(part), case.T, r, d1, d2)
+            vals.append([p["Z"], p["E"], p["Cv"]])
+        vals = np.array(vals)
+        return vals.mean(axis=0), vals.std(axis=0, ddof=1) / np.sqrt(nb)
+    (mg, eg), (mc, ec) = blocks(gpu), blocks(cpu)
+    for k, name in enumerate(("Z", "E", "Cv")):
+        assert abs(mg[k] - mc[k]) < 4.5 * np.hypot(eg[k], ec[k]), f"{name}: gpu {mg[k]} +- {eg[k]}, cpu {mc[k]} +- {ec[k]}"
+    plan.close()
+
+
+def test_mixture_frequencies_and_bead_covariance_on_device(cuda):
+    from conftest import GoldenCase
+    case = GoldenCase("jt_rho4")
+    tab = case.oracle_tables()
+    plan = case.plan()
+    X = 200000
+    R, src = drawn_coords(cuda, plan, 31337, 0, X)
+    freq = np.bincount(src, minlength=tab.Ar) / X
+    assert np.max(np.abs(freq - tab.weights)) < 4.5 * np.sqrt(0.25 / X)
+    y = R - tab.d_rho[src][:, :, None]
+    for n in range(tab.N):
+        emp = y[:, n, :].T @ y[:, n, :] / X
+        cov = (tab.ring_eigvecs * tab.sigma[n][None, :] ** 2) @ tab.ring_eigvecs.T
+        assert np.max(np.abs(emp - cov)) < 6 * np.max(np.abs(cov)) / np.sqrt(X)
+    z = y[:, 0, 0] / np.sqrt(cov[0, 0]) if tab.N == 1 else None
+    plan.close()
+
+
+# ------------------------------------------------------------------ BASELINE sizes: size-independent properties
+def test_full_size_c2_properties(cuda):
+    """A=4, N=6, P=64, X=1e6 (BASELINE.json configs[1]): the oracle cannot run this; check finiteness,
+    positivity of rho, determinism, index-split invariance, agreement of the +/- variants with g to
+    O(delta_beta), block-sum consistency (a checksum of checksums) and the mean against a small oracle run"""
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import constants, synthetic
+    from pibronic_b200.model_io import VMK
+    model = synthetic.model_c2()
+    rho = synthetic.diagonal_of(model)
+    plan = _cabi.Plan(model[VMK.E], model[VMK.w], model[VMK.G1], model[VMK.G2], rho[VMK.E], rho[VMK.w], rho[VMK.G1],
+                      64, constants.beta(300.0), constants.delta_beta, flags=_cabi.FLAG_PM, device=0)
+    assert plan.is_fast
+    X, bs = 1_000_000, 10_000
+    out, sums = plan.sample_eval_host(20260417, 0, X, block_size=bs)
+    assert np.isfinite(out).all() and (out[0] > 0).all() and (out[0] <= 4 * (1 + 1e-12)).all()
+    again, _ = plan.sample_eval_host(20260417, 0, X, block_size=bs)
+    assert np.array_equal(out, again)
+    tail = plan.sample_eval_host(20260417, X - 4097, 4097)
+    assert np.array_equal(tail, out[:, X - 4097:])
+    ratio = out[1] / out[0]
+    assert np.isclose(sums[:, 0].sum(), ratio.sum(), rtol=1e-12)
+    assert np.max(np.abs(out[2] / out[1] - 1)) < 0.05 and np.max(np.abs(out[3] / out[1] - 1)) < 0.05
+    vib_d = dict(A=4, N=6, E=model[VMK.E], w=model[VMK.w], L=model[VMK.G1], Q=model[VMK.G2])
+    rho_d = dict(A=4, N=6, E=rho[VMK.E], w=rho[VMK.w], L=rho[VMK.G1])
+    tab = orc.precompute(vib_d, rho_d, 64, 300.0)
+    cpu = orc.run_blocks(tab, 4000, 1000, np.random.RandomState(1), pm=False, faithful=False)
+    rc = cpu[1] / cpu[0]
+    err = np.hypot(ratio.std() / np.sqrt(X), rc.std() / np.sqrt(len(rc)))
+    assert abs(ratio.mean() - rc.mean()) < 4.5 * err
+    # spot-check 64 of the million samples against the oracle on the coordinates the sampler reports
+    R, _ = drawn_coords(cuda, plan, 20260417, 777_000, 64)
+    assert rel_err(out[:, 777_000:777_064], oracle_eval(tab, R)) < RTOL
+    plan.close()
+
+
+def test_c4_shape_runs_on_generic_kernels(cuda):
+    """A=12, N=24, P=256 (BASELINE.json configs[3]) at a handful of samples against the oracle"""
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import constants, synthetic
+    from pibronic_b200.model_io import VMK
+    model = synthetic.model_c4()
+    rho = synthetic.diagonal_of(model)
+    plan = _cabi.Plan(model[VMK.E], model[VMK.w], model[VMK.G1], model[VMK.G2], rho[VMK.E], rho[VMK.w], rho[VMK.G1],
+                      256, constants.beta(300.0), constants.delta_beta, flags=_cabi.FLAG_PM, device=0)
+    assert not plan.is_fast
+    n = 6
+    out = plan.sample_eval_host(1, 0, n)
+    R, _ = drawn_coords(cuda, plan, 1, 0, n)
+    vib_d = dict(A=12, N=24, E=model[VMK.E], w=model[VMK.w], L=model[VMK.G1], Q=model[VMK.G2])
+    rho_d = dict(A=12, N=24, E=rho[VMK.E], w=rho[VMK.w], L=rho[VMK.G1])
+    tab = orc.precompute(vib_d, rho_d, 256, 300.0)
+    assert rel_err(out, oracle_eval(tab, R)) < RTOL
+    plan.close()
+
+
+# ------------------------------------------------------------------ the drop-in facade end to end
+@pytest.mark.parametrize("pm", [False, True])
+def test_block_compute_through_the_facade(cuda, tmp_path, pm):
+    """mirrors the reference's smoke tests (tests/pimc/test_pimc_general.py:74-155) but WITH numeric checks:
+    FileStructure -> BoxData[PM] -> preprocess -> block_compute[_pm] -> .npz -> load_multiple_results"""
+    from os.path import isfile, join
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import file_structure, pimc, synthetic
+    FS = file_structure.FileStructure(tmp_path, 0, 0)
+    synthetic.write_data_set(FS, synthetic.coupled_model(2, 2, (0.02, 0.04), (0.1, 0.2), seed=3, linear=0.05))
+    FS.generate_model_hashes()
+    data = (pimc.BoxDataPM if pm else pimc.BoxData).from_FileStructure(FS)
+    data.samples, data.beads, data.temperature, data.block_size = 1000, 12, 300.0, 100
+    data.blocks = data.samples // data.block_size
+    data.hash_vib, data.hash_rho = FS.hash_vib, FS.hash_rho
+    data.seed = 242351
+    data.preprocess()
+    result = (pimc.BoxResultPM if pm else pimc.BoxResult)(data=data)
+    result.path_root, result.id_job = FS.path_rho_results, 3
+    (pimc.block_compute_pm if pm else pimc.block_compute)(data, result)
+    path = join(FS.path_rho_results, "P12_T300.00_J3_data_points.npz")
+    assert isfile(path)
+    loaded = type(result)()
+    loaded.load_multiple_results([path])
+    assert loaded.samples == 1000 and np.array_equal(loaded.scaled_g, result.scaled_g)
+    assert not np.isnan(result.scaled_rho).any()
+    # per-sample parity with the oracle on the coordinates of the first block (per-block sampler API)
+    view = slice(0, data.block_size)
+    data.draw_sample(view)
+    data.transform_sampled_coordinates(view)
+    R = np.ascontiguousarray(data.qTensor[:, 0])
+    tab = orc.precompute(orc.load_vibronic_json(FS.path_vib_model), orc.load_sampling_json(FS.path_rho_model), 12, 300.0)
+    want = oracle_eval(tab, R, pm=pm)
+    assert rel_err(result.scaled_rho[view], want[0]) < RTOL and rel_err(result.scaled_g[view], want[1]) < RTOL
+    if pm:
+        assert rel_err(result.scaled_gofr_plus[view], want[2]) < RTOL
+        assert rel_err(result.scaled_gofr_minus[view], want[3]) < RTOL
+    assert result.block_sums.shape == (10, _cabi.NSUMS)
+    assert np.isclose(result.block_sums[:, 0].sum(), (result.scaled_g / result.scaled_rho).sum(), rtol=1e-12)
+    data.release()
