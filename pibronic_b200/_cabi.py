@@ -10,7 +10,8 @@ from os.path import abspath, dirname, join
 
 import numpy as np
 
-_LIB_PATH = join(dirname(abspath(__file__)), "_pbx.so")
+# PBX_LIB: developer override used by the kernel experiments in tools/ (a variant build of the same sources)
+_LIB_PATH = os.environ.get("PBX_LIB") or join(dirname(abspath(__file__)), "_pbx.so")
 
 OK = 0
 FLAG_PM = 1 << 0

@@ -16,11 +16,15 @@ from os.path import abspath, dirname, join
 PKG = dirname(abspath(__file__))
 ROOT = dirname(PKG)
 CSRC = join(PKG, "csrc")
-OUT = join(PKG, "_pbx.so")
-OBJ_DIR = join(ROOT, "build", "pbx")
+# developer knobs for kernel experiments (tools/): another library name, extra -D flags, fewer shapes
+_VARIANT = os.environ.get("PBX_VARIANT", "")
+OUT = join(PKG, f"_pbx{('_' + _VARIANT) if _VARIANT else ''}.so")
+OBJ_DIR = join(ROOT, "build", "pbx" + (("_" + _VARIANT) if _VARIANT else ""))
+
 NVCC = os.environ.get("NVCC", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + \
+    os.environ.get("PBX_EXTRA_NVCC_FLAGS", "").split()
 
 
 def shapes():

@@ -295,7 +295,7 @@ int pbx_sample_eval_dev(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_
     if (p->fast) {
         FastLaunch L{};
         L.samp = p->D.samp; L.seed = seed; L.first_sample = first_sample; L.n_samples = n; L.out4 = out4; L.out_ld = n;
-        PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_SAMPLE, p->pm, p->jacobi, st));
+        PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_SAMPLE, p->pm, p->jacobi, p->H.rho_shares_vib, st));
         p->launches += 1;
         return PBX_OK;
     }
@@ -334,7 +334,7 @@ int pbx_eval_coords_dev(pbx_plan* p, const double* R, int64_t n, double* out4, v
             FastLaunch L{};
             L.samp = p->D.samp; L.coords_t = (const double*)p->scratch; L.ld = ld; L.n_samples = m;
             L.out4 = out4 + off; L.out_ld = n;
-            PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_COORDS, p->pm, p->jacobi, st));
+            PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_COORDS, p->pm, p->jacobi, p->H.rho_shares_vib, st));
             p->launches += 2;
         }
         return PBX_OK;

@@ -1,19 +1,40 @@
-// Register-resident small-A kernel: ONE SAMPLE PER THREAD, beads streamed.
+// Register-resident small-A kernel: ONE SAMPLE PER THREAD, beads streamed in tiles.
 //
-// For each sample the thread walks the ring polymer bead by bead.  Per bead it (optionally) draws
-// the next bead's coordinates (Philox + Box-Muller + ring recurrence), forms the four sets of
-// harmonic factors O (rho; vib at tau, tau+, tau-) in log space, the scaling S, the packed
-// symmetric coupling matrix V, M = exp(-tau V), and advances the three chained products
-// T_v <- (T_v M) diag(O_v).  Nothing but the 32-byte result leaves the SM.
+// For each sample the thread walks the ring polymer in tiles of PBX_TILE beads:
+//   phase S  (small rolled code): draw the tile's bead coordinates -- Philox4x32-10, FP64 Box-Muller,
+//            cyclic-tridiagonal ring recurrence -- into a per-thread column of shared memory
+//            (or, MODE_COORDS, copy caller supplied coordinates there);
+//   phase E  (fully unrolled over surfaces and modes): per bead, the four sets of harmonic factors O
+//            (rho; vib at tau, tau+, tau-) in log space, the scaling S, the packed symmetric coupling
+//            matrix V, M = exp(-tau V), and the three chained products T_v <- (T_v M) diag(O_v).
+// Splitting the phases keeps each loop body inside the instruction cache (the single fused body of
+// round 1 was ~50 KB and stalled on instruction fetch, profiles/r01_summary.md).
+// Nothing but the 32-byte result leaves the SM.
 //
-// Model constants arrive as a __grid_constant__ kernel parameter, i.e. in the constant bank:
-// after full unrolling every table element is an immediate c[0x0][..] operand of a DFMA, so the
-// coupling tables cost no load instructions and no registers.
+// Model constants arrive as a __grid_constant__ kernel parameter, i.e. in the constant bank: after
+// unrolling every table element is an LDCU'd uniform-register operand of a DFMA, so the coupling
+// tables cost no per-thread loads and no registers.
 //
 // Reference path reproduced per sample: /root/reference/pibronic/pimc/pimc.py:1420-1449
 // (block_compute_pm body) with the helpers at 1062-1213; SURVEY.md App. A.
 #pragma once
 #include "pbx_device.cuh"
+
+#ifndef PBX_BLOCK
+#define PBX_BLOCK 128        // threads per CTA
+#endif
+#ifndef PBX_MIN_BLOCKS
+#define PBX_MIN_BLOCKS 1     // __launch_bounds__ minimum CTAs per SM
+#endif
+#ifndef PBX_TILE
+#define PBX_TILE 8           // beads per tile
+#endif
+#ifndef PBX_SYNC_LOOP
+#define PBX_SYNC_LOOP 0      // 1: __syncthreads() per tile, keeps the CTA's warps in step (shared i-cache lines)
+#endif
+#ifndef PBX_DELTA_EXP
+#define PBX_DELTA_EXP 1      // 1: O(tau+-) = O(tau) * exp(delta), delta from analytic difference tables
+#endif
 
 namespace pbx {
 
@@ -25,7 +46,10 @@ struct FastTables {
     double d_rho[AR][N];
     double hc[4][N];      // -0.5 * coth  (rows: vib tau, tau+, tau-, rho)
     double cs[4][N];      // csch
+    double dhc[2][N];     // -0.5 * (coth(tau+-) - coth(tau))
+    double dcs[2][N];     // csch(tau+-) - csch(tau)
     double lpref[3][A];
+    double dlpref[2][A];
     double lpref_rho[AR];
     double wcum[AR];
     double e_off[AA];
@@ -49,22 +73,172 @@ struct FastLaunch {
 
 enum { MODE_SAMPLE = 0, MODE_COORDS = 1 };
 
-template <int A, int N, int AR, int MODE, bool PM, bool JACOBI>
-__global__ void __launch_bounds__(128)
-pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch L) {
+// exp(d) for |d| <= 2^-5 by a degree-7 Taylor polynomial (remainder < 2.3e-17)
+__device__ __forceinline__ double exp_small(double d) {
+    double p = 1.0 / 5040;
+    p = fma(p, d, 1.0 / 720);
+    p = fma(p, d, 1.0 / 120);
+    p = fma(p, d, 1.0 / 24);
+    p = fma(p, d, 1.0 / 6);
+    p = fma(p, d, 0.5);
+    p = fma(p, d, 1.0);
+    return fma(p, d, 1.0);
+}
+
+// one bead of the estimator: updates the chained products Tm and the log-accumulators of rho
+template <int A, int N, int AR, bool PM, bool JACOBI, bool SHARE>
+__device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const double (&Rc)[N], const double (&Rn)[N],
+                                          double (&Tm)[PM ? 3 : 1][A][A], double (&lrho)[AR]) {
     constexpr int AA = A * (A + 1) / 2;
     constexpr int NV = PM ? 3 : 1;
-    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= L.n_samples) return;
-    const int P = T.P;
+    // ---- harmonic factors, log space: l = logpref - 1/2 sum_n [coth (q^2+q'^2) - 2 csch q q']
+    double lv[NV][A], lr[AR];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        double e0 = 0.0;
+        double e1 = 0.0, e2 = 0.0;   // PM: tau+ / tau- sums (differences from tau when PBX_DELTA_EXP)
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            const double q = Rc[n] - T.d_vib[a][n], qn = Rn[n] - T.d_vib[a][n];
+            const double s2 = fma(q, q, qn * qn), pr = q * qn;
+            e0 = fma(T.hc[0][n], s2, fma(T.cs[0][n], pr, e0));
+            if (PM) {
+#if PBX_DELTA_EXP
+                e1 = fma(T.dhc[0][n], s2, fma(T.dcs[0][n], pr, e1));
+                e2 = fma(T.dhc[1][n], s2, fma(T.dcs[1][n], pr, e2));
+#else
+                e1 = fma(T.hc[1][n], s2, fma(T.cs[1][n], pr, e1));
+                e2 = fma(T.hc[2][n], s2, fma(T.cs[2][n], pr, e2));
+#endif
+            }
+        }
+        lv[0][a] = T.lpref[0][a] + e0;
+        if (PM) {
+#if PBX_DELTA_EXP
+            lv[1][a] = T.dlpref[0][a] + e1;   // log O(tau+) - log O(tau)
+            lv[2][a] = T.dlpref[1][a] + e2;
+#else
+            lv[1][a] = T.lpref[1][a] + e1;
+            lv[2][a] = T.lpref[2][a] + e2;
+#endif
+        }
+        if (SHARE) lr[a < AR ? a : 0] = (a < T.n_rho_eval) ? T.lpref_rho[a < AR ? a : 0] + e0 : -INFINITY;
+    }
+    if (!SHARE) {
+#pragma unroll
+        for (int a = 0; a < AR; ++a) {
+            double acc = T.lpref_rho[a];
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const double q = Rc[n] - T.d_rho[a][n], qn = Rn[n] - T.d_rho[a][n];
+                acc = fma(T.hc[3][n], fma(q, q, qn * qn), fma(T.cs[3][n], q * qn, acc));
+            }
+            lr[a] = (a < T.n_rho_eval) ? acc : -INFINITY;
+        }
+    }
+    // S = max over both models' factors (pimc.py:1076-1084), kept as a logarithm
+    double logS = lv[0][0];
+#pragma unroll
+    for (int a = 1; a < A; ++a) logS = fmax(logS, lv[0][a]);
+#pragma unroll
+    for (int a = 0; a < AR; ++a) logS = fmax(logS, lr[a]);
+#pragma unroll
+    for (int a = 0; a < AR; ++a) lrho[a] += lr[a] - logS;
+    double O[NV][A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) O[0][a] = exp(lv[0][a] - logS);
+    if (PM) {
+#if PBX_DELTA_EXP
+        double big = 0.0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) big = fmax(big, fmax(fabs(lv[1][a]), fabs(lv[2][a])));
+        if (__all_sync(__activemask(), big <= 0.03125)) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                O[1][a] = O[0][a] * exp_small(lv[1][a]);
+                O[2][a] = O[0][a] * exp_small(lv[2][a]);
+            }
+        } else {   // huge delta_beta or far-out coordinates: full exponentials
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                O[1][a] = exp(lv[0][a] + lv[1][a] - logS);
+                O[2][a] = exp(lv[0][a] + lv[2][a] - logS);
+            }
+        }
+#else
+#pragma unroll
+        for (int a = 0; a < A; ++a) { O[1][a] = exp(lv[1][a] - logS); O[2][a] = exp(lv[2][a] - logS); }
+#endif
+    }
 
-    // ---------------- sampler state
+    // ---- X = -tau * V(R_p), packed symmetric
+    double X[AA];
+#pragma unroll
+    for (int k = 0; k < AA; ++k) X[k] = 0.0;
+#pragma unroll
+    for (int i = 1; i < A; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) {
+            double acc = T.e_off[tri(i, j)];
+#pragma unroll
+            for (int n = 0; n < N; ++n) acc = fma(T.l_off[n][tri(i, j)], Rc[n], acc);
+            X[tri(i, j)] = acc;
+        }
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+        for (int m = n; m < N; ++m) {
+            const double rr = Rc[n] * Rc[m];
+#pragma unroll
+            for (int k = 0; k < AA; ++k) X[k] = fma(T.q_pack[pair_index(n, m, N)][k], rr, X[k]);
+        }
+#pragma unroll
+    for (int k = 0; k < AA; ++k) X[k] *= T.neg_tau;
+
+    double M[AA];
+    if (JACOBI) sym_exp_jacobi<A>(X, M);
+    else sym_expm<A>(X, M);
+
+    // ---- chain: T_v <- (T_v M) diag(O_v)
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            double row[A];
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                double acc = Tm[v][i][0] * M[sym(0, j)];
+#pragma unroll
+                for (int k = 1; k < A; ++k) acc = fma(Tm[v][i][k], M[sym(k, j)], acc);
+                row[j] = acc * O[v][j];
+            }
+#pragma unroll
+            for (int j = 0; j < A; ++j) Tm[v][i][j] = row[j];
+        }
+}
+
+// shared memory (doubles) per thread: (TILE+1) coordinate slots + sampler state y0, yprev, dsrc
+template <int N> constexpr int fast_smem_doubles_per_thread() { return (PBX_TILE + 1) * N + 3 * N; }
+
+template <int A, int N, int AR, int MODE, bool PM, bool JACOBI, bool SHARE>
+__global__ void __launch_bounds__(PBX_BLOCK, PBX_MIN_BLOCKS)
+pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch L) {
+    constexpr int NV = PM ? 3 : 1;
+    constexpr int TB = PBX_TILE;
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    long long x = (long long)blockIdx.x * nt + tid;
+    const bool live = x < L.n_samples;
+    if (!live) x = L.n_samples - 1;       // keep the thread in step with its CTA; its result is dropped
+    const int P = T.P;
+    // per-thread columns: element i of this thread lives at base[i * nt]
+    double* tile = smem + tid;                               // [(TB+1)][N]
+    double* y0 = smem + (size_t)(TB + 1) * N * nt + tid;     // [N] first bead relative to the source shift
+    double* yprev = y0 + (size_t)N * nt;                     // [N]
+    double* dsrc = yprev + (size_t)N * nt;                   // [N] shift of the mixture component drawn
+
     const unsigned long long gidx = (unsigned long long)(L.first_sample + x);
     const uint2 key = make_uint2((uint32_t)L.seed, (uint32_t)(L.seed >> 32));
-    double dsrc[N];   // shift of the mixture component this sample is drawn from
-    double y0[N];     // first bead, relative to dsrc (ring recurrence anchor)
-    double yprev[N];
-    double R0[N], Rc[N], Rn[N];
     if (MODE == MODE_SAMPLE) {
         const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, STREAM_SOURCE), key);
         const int src = pick_source<AR>(u01_half_open(r.x, r.y), T.wcum);
@@ -73,13 +247,20 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
             double d = T.d_rho[0][n];
 #pragma unroll
             for (int a = 1; a < AR; ++a) d = (src == a) ? T.d_rho[a][n] : d;
-            dsrc[n] = d;
+            dsrc[n * nt] = d;
         }
     }
-    auto next_bead = [&](int j, double (&R)[N]) {
+    // coordinates of bead j (j == P closes the ring: bead 0 again) into tile slot `slot`
+    auto put_bead = [&](int j, int slot) {
+        double* dst = tile + (size_t)slot * N * nt;
         if (MODE == MODE_SAMPLE) {
+            if (j == P) {
+#pragma unroll 1
+                for (int n = 0; n < N; ++n) dst[n * nt] = y0[n * nt] + dsrc[n * nt];
+                return;
+            }
             const double* tab = L.samp + (size_t)j * N * 3;
-#pragma unroll
+#pragma unroll 1
             for (int h = 0; h < (N + 1) / 2; ++h) {
                 const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32),
                                                          (uint32_t)(j * ((N + 1) / 2) + h), STREAM_NORMALS), key);
@@ -91,21 +272,20 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
                     if (n < N) {
                         const double a = __ldg(tab + n * 3 + 0), b = __ldg(tab + n * 3 + 1), e = __ldg(tab + n * 3 + 2);
                         double y = a * z[w];
-                        if (j > 0) y = fma(b, yprev[n], fma(e, y0[n], y));
-                        if (j == 0) y0[n] = y;
-                        yprev[n] = y;
-                        R[n] = y + dsrc[n];
+                        if (j > 0) y = fma(b, yprev[n * nt], fma(e, y0[n * nt], y));
+                        if (j == 0) y0[n * nt] = y;
+                        yprev[n * nt] = y;
+                        dst[n * nt] = y + dsrc[n * nt];
                     }
                 }
             }
         } else {
-            const double* src = L.coords_t + (size_t)j * L.ld + x;
-#pragma unroll
-            for (int n = 0; n < N; ++n) R[n] = __ldg(src + (size_t)n * T.P * L.ld);
+            const double* src = L.coords_t + (size_t)(j == P ? 0 : j) * L.ld + x;
+#pragma unroll 1
+            for (int n = 0; n < N; ++n) dst[n * nt] = __ldg(src + (size_t)n * P * L.ld);
         }
     };
 
-    // ---------------- accumulators
     double Tm[NV][A][A];
 #pragma unroll
     for (int v = 0; v < NV; ++v)
@@ -117,103 +297,33 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
 #pragma unroll
     for (int a = 0; a < AR; ++a) lrho[a] = 0.0;
 
-    next_bead(0, R0);
-#pragma unroll
-    for (int n = 0; n < N; ++n) Rc[n] = R0[n];
-
-    for (int p = 0; p < P; ++p) {
-        if (p + 1 < P) {
-            next_bead(p + 1, Rn);
-        } else {
-#pragma unroll
-            for (int n = 0; n < N; ++n) Rn[n] = R0[n];
-        }
-        // ---- harmonic factors, log space: l = logpref - 1/2 sum_n [coth (q^2+q'^2) - 2 csch q q']
-        double lv[NV][A], lr[AR];
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) lv[v][a] = T.lpref[v][a];
+    put_bead(0, 0);
+    for (int t0 = 0; t0 < P; t0 += TB) {
+#if PBX_SYNC_LOOP
+        __syncthreads();
+#endif
+        // ---- phase S: beads t0+1 .. t0+TB into slots 1..TB (slot 0 holds bead t0)
+#pragma unroll 1
+        for (int jj = 1; jj <= TB; ++jj)
+            if (t0 + jj <= P) put_bead(t0 + jj, jj);
+        // ---- phase E
+#pragma unroll 1
+        for (int jj = 0; jj < TB; ++jj) {
+            if (t0 + jj >= P) break;
+            double Rc[N], Rn[N];
 #pragma unroll
             for (int n = 0; n < N; ++n) {
-                const double q = Rc[n] - T.d_vib[a][n], qn = Rn[n] - T.d_vib[a][n];
-                const double s2 = fma(q, q, qn * qn), pr = q * qn;
-#pragma unroll
-                for (int v = 0; v < NV; ++v) lv[v][a] = fma(T.hc[v][n], s2, fma(T.cs[v][n], pr, lv[v][a]));
+                Rc[n] = tile[(size_t)(jj * N + n) * nt];
+                Rn[n] = tile[(size_t)((jj + 1) * N + n) * nt];
             }
+            bead_step<A, N, AR, PM, JACOBI, SHARE>(T, Rc, Rn, Tm, lrho);
         }
+        // bead t0+TB becomes slot 0 of the next tile
 #pragma unroll
-        for (int a = 0; a < AR; ++a) {
-            double acc = T.lpref_rho[a];
-#pragma unroll
-            for (int n = 0; n < N; ++n) {
-                const double q = Rc[n] - T.d_rho[a][n], qn = Rn[n] - T.d_rho[a][n];
-                acc = fma(T.hc[3][n], fma(q, q, qn * qn), fma(T.cs[3][n], q * qn, acc));
-            }
-            lr[a] = (a < T.n_rho_eval) ? acc : -INFINITY;
-        }
-        // S = max over both models' factors (pimc.py:1076-1084), kept as a logarithm
-        double logS = lv[0][0];
-#pragma unroll
-        for (int a = 1; a < A; ++a) logS = fmax(logS, lv[0][a]);
-#pragma unroll
-        for (int a = 0; a < AR; ++a) logS = fmax(logS, lr[a]);
-#pragma unroll
-        for (int a = 0; a < AR; ++a) lrho[a] += lr[a] - logS;
-        double O[NV][A];
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int a = 0; a < A; ++a) O[v][a] = exp(lv[v][a] - logS);
-
-        // ---- X = -tau * V(R_p), packed symmetric
-        double X[AA];
-#pragma unroll
-        for (int k = 0; k < AA; ++k) X[k] = 0.0;
-#pragma unroll
-        for (int i = 1; i < A; ++i)
-#pragma unroll
-            for (int j = 0; j < i; ++j) {
-                double acc = T.e_off[tri(i, j)];
-#pragma unroll
-                for (int n = 0; n < N; ++n) acc = fma(T.l_off[n][tri(i, j)], Rc[n], acc);
-                X[tri(i, j)] = acc;
-            }
-#pragma unroll
-        for (int n = 0; n < N; ++n)
-#pragma unroll
-            for (int m = n; m < N; ++m) {
-                const double rr = Rc[n] * Rc[m];
-#pragma unroll
-                for (int k = 0; k < AA; ++k) X[k] = fma(T.q_pack[pair_index(n, m, N)][k], rr, X[k]);
-            }
-#pragma unroll
-        for (int k = 0; k < AA; ++k) X[k] *= T.neg_tau;
-
-        double M[AA];
-        if (JACOBI) sym_exp_jacobi<A>(X, M);
-        else sym_expm<A>(X, M);
-
-        // ---- chain: T_v <- (T_v M) diag(O_v)
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int i = 0; i < A; ++i) {
-                double row[A];
-#pragma unroll
-                for (int j = 0; j < A; ++j) {
-                    double acc = Tm[v][i][0] * M[sym(0, j)];
-#pragma unroll
-                    for (int k = 1; k < A; ++k) acc = fma(Tm[v][i][k], M[sym(k, j)], acc);
-                    row[j] = acc * O[v][j];
-                }
-#pragma unroll
-                for (int j = 0; j < A; ++j) Tm[v][i][j] = row[j];
-            }
-#pragma unroll
-        for (int n = 0; n < N; ++n) Rc[n] = Rn[n];
+        for (int n = 0; n < N; ++n) tile[(size_t)n * nt] = tile[(size_t)(TB * N + n) * nt];
     }
 
+    if (!live) return;
     double rho = 0.0;
 #pragma unroll
     for (int a = 0; a < AR; ++a) rho += exp(lrho[a]);
@@ -232,7 +342,7 @@ struct FastKernelEntry {
     int A, N, AR;
     size_t table_bytes;
     void (*fill)(const HostTables&, void* dst);
-    cudaError_t (*launch)(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi,
+    cudaError_t (*launch)(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share,
                           cudaStream_t stream);
 };
 
@@ -243,7 +353,9 @@ void fill_fast_tables(const HostTables& H, void* dst) {
     for (int a = 0; a < A; ++a) for (int n = 0; n < N; ++n) T.d_vib[a][n] = H.d_vib[a * N + n];
     for (int a = 0; a < AR; ++a) for (int n = 0; n < N; ++n) T.d_rho[a][n] = H.d_rho[a * N + n];
     for (int v = 0; v < 4; ++v) for (int n = 0; n < N; ++n) { T.hc[v][n] = -0.5 * H.coth[v * N + n]; T.cs[v][n] = H.csch[v * N + n]; }
+    for (int v = 0; v < 2; ++v) for (int n = 0; n < N; ++n) { T.dhc[v][n] = -0.5 * H.dcoth[v * N + n]; T.dcs[v][n] = H.dcsch[v * N + n]; }
     for (int v = 0; v < 3; ++v) for (int a = 0; a < A; ++a) T.lpref[v][a] = H.logpref[v * A + a];
+    for (int v = 0; v < 2; ++v) for (int a = 0; a < A; ++a) T.dlpref[v][a] = H.dlogpref[v * A + a];
     for (int a = 0; a < AR; ++a) { T.lpref_rho[a] = H.logpref_rho[a]; T.wcum[a] = H.wcum[a]; }
     for (int k = 0; k < AA; ++k) T.e_off[k] = H.e_off[k];
     for (int n = 0; n < N; ++n) for (int k = 0; k < AA; ++k) T.l_off[n][k] = H.l_off[(size_t)n * AA + k];
@@ -253,23 +365,37 @@ void fill_fast_tables(const HostTables& H, void* dst) {
     T.n_rho_eval = H.n_rho_eval;
 }
 
-template <int A, int N, int AR, int MODE, bool PM, bool JACOBI>
+template <int A, int N, int AR, int MODE, bool PM, bool JACOBI, bool SHARE>
 cudaError_t launch_one(const FastTables<A, N, AR>& T, const FastLaunch& L, cudaStream_t stream) {
-    const int threads = 128;
+    const int threads = PBX_BLOCK;
     const long long blocks = (L.n_samples + threads - 1) / threads;
-    pbx_fast_kernel<A, N, AR, MODE, PM, JACOBI><<<(unsigned)blocks, threads, 0, stream>>>(T, L);
+    const size_t smem = (size_t)fast_smem_doubles_per_thread<N>() * threads * sizeof(double);
+    auto kernel = pbx_fast_kernel<A, N, AR, MODE, PM, JACOBI, SHARE>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kernel<<<(unsigned)blocks, threads, smem, stream>>>(T, L);
     return cudaGetLastError();
 }
 
+template <int A, int N, int AR, int MODE, bool PM, bool JACOBI>
+cudaError_t launch_share(const FastTables<A, N, AR>& T, const FastLaunch& L, bool share, cudaStream_t stream) {
+    if constexpr (A == AR) {
+        if (share) return launch_one<A, N, AR, MODE, PM, JACOBI, true>(T, L, stream);
+    }
+    return launch_one<A, N, AR, MODE, PM, JACOBI, false>(T, L, stream);
+}
+
 template <int A, int N, int AR>
-cudaError_t launch_fast(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi,
+cudaError_t launch_fast(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share,
                         cudaStream_t stream) {
     const auto& T = *reinterpret_cast<const FastTables<A, N, AR>*>(tables);
-#define PBX_DISPATCH(MODE_)                                                                        \
-    if (pm) return jacobi ? launch_one<A, N, AR, MODE_, true, true>(T, L, stream)                  \
-                          : launch_one<A, N, AR, MODE_, true, false>(T, L, stream);                \
-    return jacobi ? launch_one<A, N, AR, MODE_, false, true>(T, L, stream)                         \
-                  : launch_one<A, N, AR, MODE_, false, false>(T, L, stream);
+#define PBX_DISPATCH(MODE_)                                                                               \
+    if (pm) return jacobi ? launch_share<A, N, AR, MODE_, true, true>(T, L, share, stream)               \
+                          : launch_share<A, N, AR, MODE_, true, false>(T, L, share, stream);             \
+    return jacobi ? launch_share<A, N, AR, MODE_, false, true>(T, L, share, stream)                      \
+                  : launch_share<A, N, AR, MODE_, false, false>(T, L, share, stream);
     if (mode == MODE_SAMPLE) { PBX_DISPATCH(MODE_SAMPLE) }
     PBX_DISPATCH(MODE_COORDS)
 #undef PBX_DISPATCH
@@ -280,7 +406,7 @@ constexpr FastKernelEntry make_entry() {
     return FastKernelEntry{A, N, AR, sizeof(FastTables<A, N, AR>), &fill_fast_tables<A, N, AR>, &launch_fast<A, N, AR>};
 }
 
-// defined in pbx_fast_*.cu
+// defined in pbx_fast_registry.cu
 const FastKernelEntry* find_fast_kernel(int A, int N, int AR);
 
 }  // namespace pbx

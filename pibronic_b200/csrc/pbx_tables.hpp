@@ -33,12 +33,20 @@ struct HostTables {
     std::vector<double> d_vib, d_rho, delta_vib, delta_rho, weights, wcum;
     std::vector<double> coth, csch;       // [4][N]: vib tau, vib tau+, vib tau-, rho tau (rho's own omega)
     std::vector<double> logpref;          // [3][A]
+    // differences of the tau+ / tau- tables from the tau ones, formed analytically (not by subtracting
+    // rounded doubles): rows 0 = tau+ - tau, 1 = tau- - tau.  Used to get O(tau+-) = O(tau) * exp(delta).
+    std::vector<double> dcoth, dcsch;     // [2][N]
+    std::vector<double> dlogpref;         // [2][A]
     std::vector<double> logpref_rho;      // [Ar]
     std::vector<double> e_off;            // [AA]   diagonal entries zero
     std::vector<double> l_off;            // [N][AA] diagonal entries zero
     std::vector<double> q_pack;           // [NN][AA] 0.5*(Q[n,m]+Q[m,n]) for n<m, 0.5*Q[n,n] for n==m
     std::vector<double> samp;             // [P][N][3]: a, b, e of y_j = a z + b y_{j-1} + e y_0
     bool has_quadratic = false;
+    // true when sampling surface a has the same shift and frequencies as system surface a for every
+    // a < min(A, Ar) -- e.g. rho = diagonal of the model (vIO.create_basic_diagonal_model): the harmonic
+    // exponent sums of rho and of the tau variant are then the same numbers
+    bool rho_shares_vib = false;
 };
 
 inline bool close_enough(double x, double y) { return std::fabs(x - y) <= 1e-8 + 1e-5 * std::fabs(y); }
@@ -161,6 +169,22 @@ inline int build_tables(const pbx_model* vib, const pbx_rho* rho, int P, double 
         if (v < 3) for (int a = 0; a < A; ++a) T.logpref[v * A + a] = (double)(-t * tilde[a] + half_log_csch);
         else for (int a = 0; a < Ar; ++a) T.logpref_rho[a] = (double)(-t * tilde_r[a] + half_log_csch);
     }
+    // ---- analytic differences between the tau+/- and tau tables of the vibronic model
+    T.dcoth.assign(2 * N, 0.0); T.dcsch.assign(2 * N, 0.0); T.dlogpref.assign(2 * A, 0.0);
+    for (int v = 1; v < 3; ++v) {
+        const long double t0 = T.tau[0], tv = T.tau[v];
+        long double half_dlog = 0.0L;
+        for (int n = 0; n < N; ++n) {
+            const long double a = t0 * (long double)vib->omega[n], b = tv * (long double)vib->omega[n];
+            const long double sa = std::sinh(a), sb = std::sinh(b);
+            // coth(b) - coth(a) = sinh(a - b) / (sinh a sinh b);  csch(b) - csch(a) = (sinh a - sinh b) / (sinh a sinh b)
+            const long double dsinh = 2.0L * std::cosh(0.5L * (a + b)) * std::sinh(0.5L * (b - a));  // sinh b - sinh a
+            T.dcoth[(v - 1) * N + n] = (double)(std::sinh(a - b) / (sa * sb));
+            T.dcsch[(v - 1) * N + n] = (double)(-dsinh / (sa * sb));
+            half_dlog += -0.5L * std::log1p(dsinh / sa);   // -1/2 log(sinh b / sinh a)
+        }
+        for (int a = 0; a < A; ++a) T.dlogpref[(v - 1) * A + a] = (double)(-(tv - t0) * tilde[a] + half_dlog);
+    }
     // ---- packed coupling tables: what is left in V after the fold (pimc.py:208-218, 1147-1160);
     //      lower triangle, like np.linalg.eigh(UPLO='L') reads it
     T.e_off.assign(T.AA, 0.0); T.l_off.assign((size_t)N * T.AA, 0.0); T.q_pack.assign((size_t)T.NN * T.AA, 0.0);
@@ -178,6 +202,12 @@ inline int build_tables(const pbx_model* vib, const pbx_rho* rho, int P, double 
                     if (q != 0.0) T.has_quadratic = true;
                 }
         }
+    T.rho_shares_vib = (Ar == A);
+    for (int n = 0; n < N && T.rho_shares_vib; ++n) {
+        if (vib->omega[n] != rho->omega[n]) T.rho_shares_vib = false;
+        for (int a = 0; a < A && a < Ar; ++a)
+            if (T.d_vib[a * N + n] != T.d_rho[a * N + n]) T.rho_shares_vib = false;
+    }
     // ---- sampler recurrence, one (a,b,e) triple per (bead, mode); precision = 2coth - csch*C
     T.samp.assign((size_t)P * N * 3, 0.0);
     std::vector<long double> a, b, e;

@@ -38,8 +38,16 @@ def time_plan(plan, X, reps=3):
 
 def main():
     X = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
-    print("fp64 peak (DFMA probe): %.2f TFLOP/s" % _cabi.fp64_peak_tflops(0))
     model = synthetic.model_c2()
+    if "--quick" in sys.argv:
+        import os
+        plan = make_plan(model, 64, 300.0, _cabi.FLAG_PM)
+        ms, out = time_plan(plan, X, reps=5)
+        o = out.cpu().numpy()
+        print(f"{os.environ.get('PBX_LIB', 'default'):40s} c2 expm PM X={X} {ms:8.3f} ms  {X * 64 / ms * 1e3:.3e} samples*beads/s "
+              f"<g/rho>={(o[1] / o[0]).mean():.5f}")
+        return
+    print("fp64 peak (DFMA probe): %.2f TFLOP/s" % _cabi.fp64_peak_tflops(0))
     for name, flags in (("expm", _cabi.FLAG_PM), ("jacobi", _cabi.FLAG_PM | _cabi.FLAG_EIG_JACOBI),
                         ("expm nonPM", 0)):
         plan = make_plan(model, 64, 300.0, flags)
