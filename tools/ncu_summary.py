@@ -1,0 +1,49 @@
+"""Prints the key metrics of an ncu report (run where ncu is installed; no GPU needed).
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [out.csv]
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEEP = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor', 'launch__grid_size', 'launch__block_size',
+        'launch__shared_mem_per_block_dynamic',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__inst_executed.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second',
+        'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed',
+        'sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained',
+        'smsp__sass_inst_executed_op_local_ld.sum', 'smsp__sass_inst_executed_op_local_st.sum',
+        'smsp__sass_inst_executed_op_shared_ld.sum', 'smsp__sass_inst_executed_op_shared_st.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    out = []
+    for vals in rows[2:]:
+        for h, u, v in zip(hdr, units, vals):
+            if h in KEEP or ('issue_stalled' in h and 'per_issue_active' in h) or h in ('Kernel Name', 'Grid Size', 'Block Size'):
+                out.append((h, u, v))
+    for h, u, v in out:
+        print(f"{h:85s} {u:16s} {v}")
+    if len(sys.argv) > 2:
+        with open(sys.argv[2], "w") as fh:
+            w = csv.writer(fh)
+            w.writerow(["metric", "unit", "value"])
+            w.writerows(out)
+
+
+if __name__ == "__main__":
+    main()
