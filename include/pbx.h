@@ -21,6 +21,7 @@
  *   pbx_sample_coords    draw_sample + transform_sampled_coordinates only      pimc.py:326-334, 613-631
  *   pbx_chain_trace      build_numerator's bead chain on caller supplied M and O          pimc.py:1194-1209
  *   pbx_block_sums       per-block sums consumed by pibronic/stats/stats.py:38-55, 84-123
+ *   pbx_stats_*          basic_jackknife_analysis                       stats/stats.py:271-299, jackknife.py:60-105
  *
  * Conventions
  *   - plain C: pointers + sizes, no C++/torch types.  All arrays are IEEE float64, C order.
@@ -149,6 +150,18 @@ int pbx_chain_trace_dev(pbx_plan *plan, const double *m_mat, const double *o_dia
  * Deterministic (fixed summation order). */
 int pbx_block_sums_dev(pbx_plan *plan, const double *out4_dev, int64_t n_samples, int64_t block_size,
                        double *sums_dev, void *stream);
+
+/* On-device Z, E, Cv and their leave-one-out jackknife (what stats.basic_jackknife_analysis computes from the
+ * four arrays, pibronic/stats/stats.py:38-55, 84-123, 271-299 and jackknife.py:60-105), WITHOUT the harmonic
+ * contribution of the sampling model (the caller adds E_sampling / Cv_sampling).  Needs a PBX_FLAG_PM plan.
+ *   stats_host[PBX_NSTATS] = Z, Z error, E, E error (0), Cv, Cv error (0), jk_E, jk_E error, jk_Cv, jk_Cv error
+ * pbx_stats_dev : out4 is a DEVICE [4][n] array (row stride n); synchronises `stream`.
+ * pbx_stats_host: out4 is a HOST array with row stride ld_host (copied to the device first).
+ * pbx_stats_last: statistics of the most recent *_host call, from its device-resident copy (no transfer). */
+#define PBX_NSTATS 10
+int pbx_stats_dev(pbx_plan *plan, const double *out4_dev, int64_t n_samples, double *stats_host, void *stream);
+int pbx_stats_host(pbx_plan *plan, const double *out4_host, int64_t ld_host, int64_t n_samples, double *stats_host);
+int pbx_stats_last(pbx_plan *plan, double *stats_host);
 
 /* Measured FP64 FMA throughput of the device in TFLOP/s (dependent-chain DFMA micro-kernel);
  * the roofline denominator used by bench.py. */

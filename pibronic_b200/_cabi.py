@@ -22,6 +22,8 @@ FLAG_FORCE_GENERIC = 1 << 4
 FLAG_NO_SCALING = 1 << 5
 NSUMS = 8
 SUM_NAMES = ("r", "r_plus", "r_minus", "r_sq", "d1", "d2", "d1_sq", "d2_sq")
+NSTATS = 10
+STAT_NAMES = ("Z", "Z error", "E", "E error", "Cv", "Cv error", "jk_E", "jk_E error", "jk_Cv", "jk_Cv error")
 
 _dp = C.POINTER(C.c_double)
 
@@ -73,6 +75,9 @@ def lib():
         "pbx_eval_stages_dev": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp, vp]),
         "pbx_chain_trace_dev": (C.c_int, [vp, vp, vp, i64, vp, vp]),
         "pbx_block_sums_dev": (C.c_int, [vp, vp, i64, i64, vp, vp]),
+        "pbx_stats_dev": (C.c_int, [vp, vp, i64, _dp, vp]),
+        "pbx_stats_host": (C.c_int, [vp, vp, i64, i64, _dp]),
+        "pbx_stats_last": (C.c_int, [vp, _dp]),
         "pbx_fp64_peak_tflops": (C.c_int, [i32, _dp]),
     }
     for name, (res, args) in sigs.items():
@@ -85,7 +90,8 @@ def lib():
 EXPORTED_SYMBOLS = ("pbx_abi_version", "pbx_last_error", "pbx_device_count", "pbx_plan_create", "pbx_plan_destroy",
                     "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_launch_count", "pbx_sample_eval_dev",
                     "pbx_sample_eval_host", "pbx_eval_coords_dev", "pbx_eval_coords_host", "pbx_sample_coords_dev",
-                    "pbx_eval_stages_dev", "pbx_chain_trace_dev", "pbx_block_sums_dev", "pbx_fp64_peak_tflops")
+                    "pbx_eval_stages_dev", "pbx_chain_trace_dev", "pbx_block_sums_dev", "pbx_stats_dev", "pbx_stats_host",
+                    "pbx_stats_last", "pbx_fp64_peak_tflops")
 
 
 def _check(rc):
@@ -203,6 +209,31 @@ class Plan:
     def block_sums(self, out4, n_samples, block_size, sums, stream=None):
         _check(lib().pbx_block_sums_dev(self._handle, _devptr(out4), int(n_samples), int(block_size), _devptr(sums),
                                         _stream_handle(stream)))
+
+    # ---- statistics (Z, E, Cv + jackknife, without the sampling model's harmonic contribution)
+    def _stats_dict(self, values):
+        return dict(zip(STAT_NAMES, (float(v) for v in values)))
+
+    def stats(self, out4, n_samples=None, stream=None):
+        """from a device [4][n] tensor"""
+        values = (C.c_double * NSTATS)()
+        n = int(out4.shape[1] if n_samples is None else n_samples)
+        _check(lib().pbx_stats_dev(self._handle, _devptr(out4), n, values, _stream_handle(stream)))
+        return self._stats_dict(values)
+
+    def stats_host(self, out4):
+        """from a host (4, n) array with contiguous rows"""
+        out4, ld = self._host_out(out4, out4.shape[1])
+        assert out4.shape[0] == 4
+        values = (C.c_double * NSTATS)()
+        _check(lib().pbx_stats_host(self._handle, out4.ctypes.data, int(ld), int(out4.shape[1]), values))
+        return self._stats_dict(values)
+
+    def stats_last(self):
+        """of the most recent *_host call (its results are still on the device)"""
+        values = (C.c_double * NSTATS)()
+        _check(lib().pbx_stats_last(self._handle, values))
+        return self._stats_dict(values)
 
     # ---- host entry points (numpy arrays; copies happen inside the library)
     @staticmethod

@@ -1,5 +1,6 @@
 // C ABI of the pbx library (include/pbx.h): plan management, launch orchestration, reductions.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -77,6 +78,65 @@ pbx_block_sums_kernel(const double* __restrict__ out4, long long ld, long long n
     if (threadIdx.x < PBX_NSUMS) sums[blk * PBX_NSUMS + threadIdx.x] = sh[threadIdx.x][0];
 }
 
+// ---- statistics: sums for Z, E, Cv and the leave-one-out jackknife (stats.py:38-123, jackknife.py:60-105) ----
+constexpr int kStatGrid = 592;   // 4 CTAs per SM; partials are added on the host in a fixed order
+
+__device__ __forceinline__ void stat_terms(const double* __restrict__ out4, long long ld, long long x, double inv2db,
+                                           double invdb2, double& r, double& d1, double& d2) {
+    const double rho = out4[x], g = out4[ld + x], gp = out4[2 * ld + x], gm = out4[3 * ld + x];
+    r = g / rho;
+    d1 = (gp - gm) / rho * inv2db;
+    d2 = (gp - 2.0 * g + gm) / rho * invdb2;
+}
+
+template <int K>
+__device__ __forceinline__ void cta_reduce_store(double (&acc)[K], double* __restrict__ partials) {
+    __shared__ double sh[K][256];
+#pragma unroll
+    for (int k = 0; k < K; ++k) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+#pragma unroll
+            for (int k = 0; k < K; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < K) partials[blockIdx.x * K + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// partials[grid][4]: sum r, sum r^2, sum d1, sum d2
+__global__ void __launch_bounds__(256)
+pbx_stat_sums_kernel(const double* __restrict__ out4, long long ld, long long n, double inv2db, double invdb2,
+                     double* __restrict__ partials) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long x = (long long)blockIdx.x * 256 + threadIdx.x; x < n; x += (long long)gridDim.x * 256) {
+        double r, d1, d2;
+        stat_terms(out4, ld, x, inv2db, invdb2, r, d1, d2);
+        acc[0] += r; acc[1] = fma(r, r, acc[1]); acc[2] += d1; acc[3] += d2;
+    }
+    cta_reduce_store<4>(acc, partials);
+}
+
+// leave-one-out estimators f_E, f_C of every sample, accumulated relative to the shifts kE, kC (the full-sample
+// values, within O(1/X) of every f) so that the variance does not cancel.  partials[grid][4]: sum dE, dE^2, dC, dC^2
+__global__ void __launch_bounds__(256)
+pbx_jackknife_kernel(const double* __restrict__ out4, long long ld, long long n, double inv2db, double invdb2,
+                     double S_r, double S_1, double S_2, double inv_kbt2, double kE, double kC,
+                     double* __restrict__ partials) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const double inv_nm1 = 1.0 / (double)(n - 1);
+    for (long long x = (long long)blockIdx.x * 256 + threadIdx.x; x < n; x += (long long)gridDim.x * 256) {
+        double r, d1, d2;
+        stat_terms(out4, ld, x, inv2db, invdb2, r, d1, d2);
+        const double jr = (S_r - r) * inv_nm1, j1 = (S_1 - d1) * inv_nm1, j2 = (S_2 - d2) * inv_nm1;
+        const double fE = -j1 / jr;
+        const double fC = (j2 / jr - fE * fE) * inv_kbt2;
+        const double dE = fE - kE, dC = fC - kC;
+        acc[0] += dE; acc[1] = fma(dE, dE, acc[1]); acc[2] += dC; acc[3] = fma(dC, dC, acc[3]);
+    }
+    cta_reduce_store<4>(acc, partials);
+}
+
 // ---- FP64 peak probe: 8 independent dependent-FMA chains per thread ------------------------------
 __global__ void __launch_bounds__(256) pbx_dfma_probe_kernel(double* out, int iters, double a, double b) {
     double v[8];
@@ -106,6 +166,8 @@ struct pbx_plan {
     size_t scratch_bytes = 0;
     void* io = nullptr;  // device staging for the *_host entry points
     size_t io_bytes = 0;
+    long long io_samples = 0;      // samples of the last *_host call still resident in `io` ([4][io_samples])
+    double* stat_partials = nullptr;
     cudaStream_t own_stream = nullptr;
     long long launches = 0;
 };
@@ -258,6 +320,7 @@ int pbx_plan_destroy(pbx_plan* p) {
     if (p->dev_tables) cudaFree(p->dev_tables);
     if (p->scratch) cudaFree(p->scratch);
     if (p->io) cudaFree(p->io);
+    if (p->stat_partials) cudaFree(p->stat_partials);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
     return PBX_OK;
@@ -421,6 +484,7 @@ int pbx_sample_eval_host(pbx_plan* p, uint64_t seed, int64_t first_sample, int64
     if (rc != PBX_OK) return rc;
     double* out_dev = (double*)p->io;
     double* sums_dev = out_dev + (size_t)4 * n;
+    p->io_samples = n;
     rc = pbx_sample_eval_dev(p, seed, first_sample, n, out_dev, p->own_stream);
     if (rc != PBX_OK) return rc;
     if (sums_host) {
@@ -449,6 +513,7 @@ int pbx_eval_coords_host(pbx_plan* p, const double* R_host, int64_t n, double* o
     if (rc != PBX_OK) return rc;
     double* out_dev = (double*)p->io;
     double* R_dev = out_dev + (size_t)4 * n;
+    p->io_samples = n;
     PBX_CUDA(cudaMemcpyAsync(R_dev, R_host, n * np * sizeof(double), cudaMemcpyHostToDevice, p->own_stream));
     rc = pbx_eval_coords_dev(p, R_dev, n, out_dev, p->own_stream);
     if (rc != PBX_OK) return rc;
@@ -457,6 +522,75 @@ int pbx_eval_coords_host(pbx_plan* p, const double* R_host, int64_t n, double* o
                                cudaMemcpyDeviceToHost, p->own_stream));
     PBX_CUDA(cudaStreamSynchronize(p->own_stream));
     return PBX_OK;
+}
+
+int pbx_stats_dev(pbx_plan* p, const double* out4, int64_t n, double* stats_host, void* stream) {
+    if (!p || !out4 || !stats_host) return fail(PBX_ERR_ARG, "null argument");
+    if (n < 2) return fail(PBX_ERR_ARG, "statistics need at least 2 samples");
+    if (!p->pm) return fail(PBX_ERR_ARG, "statistics need a PBX_FLAG_PM plan (g+ and g-)");
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->stat_partials) PBX_CUDA(cudaMalloc((void**)&p->stat_partials, kStatGrid * 4 * sizeof(double)));
+    const double db = p->H.delta_beta, inv2db = 1.0 / (2.0 * db), invdb2 = 1.0 / (db * db);
+    const double kB = 1.38064852e-23 / 1.6021766208e-19;        // pibronic/constants.py:12,24
+    const double T = 1.0 / (kB * p->H.beta), kbt2 = kB * T * T;
+    double part[kStatGrid * 4];
+    auto total = [&](int col) {
+        long double acc = 0.0L;
+        for (int b = 0; b < kStatGrid; ++b) acc += part[b * 4 + col];
+        return acc;
+    };
+    pbx_stat_sums_kernel<<<kStatGrid, 256, 0, st>>>(out4, n, n, inv2db, invdb2, p->stat_partials);
+    PBX_CUDA(cudaGetLastError());
+    PBX_CUDA(cudaMemcpyAsync(part, p->stat_partials, sizeof(part), cudaMemcpyDeviceToHost, st));
+    PBX_CUDA(cudaStreamSynchronize(st));
+    const long double X = (long double)n, S_r = total(0), S_rr = total(1), S_1 = total(2), S_2 = total(3);
+    const long double Z = S_r / X;
+    long double var = S_rr / X - Z * Z;
+    if (var < 0) var = 0;
+    const long double E = -(S_1 / X) / Z;
+    const long double Cv = ((S_2 / X) / Z - E * E) / kbt2;
+    pbx_jackknife_kernel<<<kStatGrid, 256, 0, st>>>(out4, n, n, inv2db, invdb2, (double)S_r, (double)S_1, (double)S_2,
+                                                   1.0 / kbt2, (double)E, (double)Cv, p->stat_partials);
+    PBX_CUDA(cudaGetLastError());
+    PBX_CUDA(cudaMemcpyAsync(part, p->stat_partials, sizeof(part), cudaMemcpyDeviceToHost, st));
+    PBX_CUDA(cudaStreamSynchronize(st));
+    p->launches += 2;
+    const long double sE = total(0), sEE = total(1), sC = total(2), sCC = total(3);
+    const long double mean_fE = (long double)(double)E + sE / X, mean_fC = (long double)(double)Cv + sC / X;
+    long double var_fE = (sEE - sE * sE / X) / (X - 1), var_fC = (sCC - sC * sC / X) / (X - 1);
+    if (var_fE < 0) var_fE = 0;
+    if (var_fC < 0) var_fC = 0;
+    stats_host[0] = (double)Z;
+    stats_host[1] = (double)(std::sqrt(var) / std::sqrt(X - 1));
+    stats_host[2] = (double)E;  stats_host[3] = 0.0;
+    stats_host[4] = (double)Cv; stats_host[5] = 0.0;
+    stats_host[6] = (double)(X * E - (X - 1) * mean_fE);
+    stats_host[7] = (double)(std::sqrt(X - 1) * std::sqrt(var_fE));
+    stats_host[8] = (double)(X * Cv - (X - 1) * mean_fC);
+    stats_host[9] = (double)(std::sqrt(X - 1) * std::sqrt(var_fC));
+    return PBX_OK;
+}
+
+int pbx_stats_host(pbx_plan* p, const double* out4_host, int64_t ld_host, int64_t n, double* stats_host) {
+    if (!p || !out4_host || !stats_host) return fail(PBX_ERR_ARG, "null argument");
+    if (n < 2 || ld_host < n) return fail(PBX_ERR_ARG, "need n >= 2 and ld_host >= n");
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    int rc = ensure(&p->io, &p->io_bytes, (size_t)4 * n * sizeof(double));
+    if (rc != PBX_OK) return rc;
+    PBX_CUDA(cudaMemcpy2DAsync(p->io, n * sizeof(double), out4_host, ld_host * sizeof(double), n * sizeof(double), 4,
+                               cudaMemcpyHostToDevice, p->own_stream));
+    p->io_samples = n;
+    return pbx_stats_dev(p, (const double*)p->io, n, stats_host, p->own_stream);
+}
+
+int pbx_stats_last(pbx_plan* p, double* stats_host) {
+    if (!p || !stats_host) return fail(PBX_ERR_ARG, "null argument");
+    PBX_NEED_DEVICE(p);
+    if (p->io_samples < 2) return fail(PBX_ERR_ARG, "no device-resident results: call a *_host entry point first");
+    return pbx_stats_dev(p, (const double*)p->io, p->io_samples, stats_host, p->own_stream);
 }
 
 int pbx_fp64_peak_tflops(int32_t device, double* tflops_out) {

@@ -132,8 +132,31 @@ def pack_explicit_kat():
     print("explicit_kat.npz:", ", ".join(f"{k}{getattr(v, 'shape', '')}" for k, v in out.items()))
 
 
+def pack_stats_kat():
+    """the reference's basic_jackknife_analysis on arrays the reference itself produced (X=3000, P=7)"""
+    from pibronic.stats import stats as ref_stats
+    case_dir = join(HERE, "cases", "quad_3x4")
+    out = run_reference(join(case_dir, "coupled_model.json"), join(case_dir, "sampling_model.json"),
+                        P=7, T=250.0, X=3000, B=1000, seed=21)
+
+    class Holder:
+        pass
+    res = Holder()
+    res.scaled_rho, res.scaled_g, res.scaled_gofr_plus, res.scaled_gofr_minus = (out[k] for k in ("s_rho", "s_g", "s_gP", "s_gM"))
+    res.samples = 3000
+    analytic = {"E": 0.0123, "Cv": 4.5e-5}
+    expected = ref_stats.basic_jackknife_analysis(250.0, res, dict(analytic))
+    basic = ref_stats.basic_statistical_analysis(250.0, res, dict(analytic))
+    np.savez_compressed(join(HERE, "stats_kat.npz"), s_rho=out["s_rho"], s_g=out["s_g"], s_gP=out["s_gP"], s_gM=out["s_gM"],
+                        T=250.0, E_sampling=analytic["E"], Cv_sampling=analytic["Cv"],
+                        keys=np.array(sorted(expected)), values=np.array([expected[k] for k in sorted(expected)]),
+                        basic_keys=np.array(sorted(basic)), basic_values=np.array([basic[k] for k in sorted(basic)]))
+    print("stats_kat.npz:", {k: float(v) for k, v in expected.items()})
+
+
 def main():
     pack_explicit_kat()
+    pack_stats_kat()
     ex = join(REFERENCE, "examples")
     # c1: 2 surfaces x 2 modes, linear diagonal coupling only, P=12 (BASELINE.json configs[0])
     write_case("c1_2x2", join(ex, "artificial_systems/input_json/model_2x2.json"), None, P=12, T=300.0, X=24, B=8, seed=11)

@@ -398,3 +398,76 @@ def test_block_compute_through_the_facade(cuda, tmp_path, pm):
     assert result.block_sums.shape == (10, _cabi.NSUMS)
     assert np.isclose(result.block_sums[:, 0].sum(), (result.scaled_g / result.scaled_rho).sum(), rtol=1e-12)
     data.release()
+
+
+# ------------------------------------------------------------------ "next" rows: statistics, analytic data, sweep
+def test_device_statistics_match_the_reference(cuda):
+    """pbx_stats_* against the reference's basic_jackknife_analysis output (golden/stats_kat.npz)"""
+    from os.path import join
+    from conftest import GOLDEN
+    from pibronic_b200 import pimc, stats
+    kat = np.load(join(GOLDEN, "stats_kat.npz"))
+    res = pimc.BoxResultPM(X=3000)
+    res.scaled_rho[:], res.scaled_g[:] = kat["s_rho"], kat["s_g"]
+    res.scaled_gofr_plus[:], res.scaled_gofr_minus[:] = kat["s_gP"], kat["s_gM"]
+    analytic_data = {"E": float(kat["E_sampling"]), "Cv": float(kat["Cv_sampling"])}
+    got = stats.basic_jackknife_analysis(float(kat["T"]), res, analytic_data)
+    want = dict(zip((str(k) for k in kat["keys"]), kat["values"]))
+    assert set(got) == set(want)
+    for key in want:
+        tol = 1e-7 if key.startswith("jk_") else 1e-11     # X*E - (X-1)*mean(f) cancels log10(X) digits in both
+        assert np.isclose(got[key], want[key], rtol=tol, atol=1e-300), f"{key}: {got[key]} vs {want[key]}"
+    basic = stats.basic_statistical_analysis(float(kat["T"]), res, analytic_data)
+    want_basic = dict(zip((str(k) for k in kat["basic_keys"]), kat["basic_values"]))
+    assert set(basic) == set(want_basic)
+    for key in want_basic:
+        assert np.isclose(basic[key], want_basic[key], rtol=1e-11, atol=1e-300), key
+
+
+def test_device_statistics_at_scale_match_oracle(cuda):
+    """1e6 samples straight from the device-resident results of the last run vs the numpy restatement"""
+    from oracle import stats_oracle
+    from conftest import GoldenCase
+    case = GoldenCase("quad_3x4")
+    plan = case.plan()
+    X = 1_000_000
+    out = plan.sample_eval_host(5, 0, X)
+    got = plan.stats_last()
+    want = stats_oracle.basic_jackknife_analysis(case.T, *out)
+    for key, value in want.items():
+        tol = 2e-6 if key in ("jk_E", "jk_Cv") else 1e-9
+        assert np.isclose(got[key], value, rtol=tol, atol=1e-300), f"{key}: {got[key]} vs {value}"
+    with cuda.cuda.device(0):
+        dev = cuda.from_numpy(out).cuda()
+        again = plan.stats(dev)
+    assert again == got
+    plan.close()
+
+
+def test_sweep_statistics_and_thermo_files(cuda, tmp_path):
+    """temperature x bead sweep -> .npz shards -> analytic_results.json -> jackknife -> *_thermo files"""
+    import json
+    from os.path import isfile
+    from pibronic_b200 import file_structure, stats, sweep, synthetic
+    FS = file_structure.FileStructure(tmp_path, 0, 0)
+    synthetic.write_data_set(FS, synthetic.coupled_model(2, 2, (0.02, 0.04), (0.1, 0.2), seed=3, linear=0.05))
+    params = {"temperature_list": [250.0, 300.0], "bead_list": [8, 12], "number_of_samples": 20000,
+              "block_size": 1000, "seed": 11}
+    results = sweep.run_sweep(FS, params)
+    assert set(results) == {(8, 250.0), (8, 300.0), (12, 250.0), (12, 300.0)}
+    thermo = stats.jackknife_analysis_of_pimc(FS, method="basic")
+    assert set(thermo) == set(results)
+    for (P, T), out in thermo.items():
+        path = FS.template_jackknife.format(P=P, T=T, X=20000)
+        assert isfile(path)
+        with open(path) as fh:
+            stored = json.load(fh)
+        assert stored["hash_vib"] == FS.hash_vib and stored["Z"] == out["Z"]
+        assert set(stored) == {"Z", "Z error", "E", "E error", "Cv", "Cv error", "jk_E", "jk_E error", "jk_Cv",
+                               "jk_Cv error", "hash_vib", "hash_rho"}
+        assert abs(stored["jk_E"] - stored["E"]) < 5 * stored["jk_E error"] + 1e-12
+        assert stored["Z"] > 0 and stored["Z error"] < 0.05 * stored["Z"]
+    # colder -> lower energy
+    assert thermo[(12, 250.0)]["E"] < thermo[(12, 300.0)]["E"]
+    with pytest.raises(Exception, match="Invalid value for parameter method"):
+        stats.statistical_analysis_of_pimc(FS, method="alpha")
