@@ -9,6 +9,7 @@
 
 #include "pbx_fast.cuh"
 #include "pbx_generic.cuh"
+#include "pbx_mid.cuh"
 
 using namespace pbx;
 
@@ -208,6 +209,48 @@ size_t generic_doubles_per_sample(const HostTables& H) {
     return (size_t)H.P * ((size_t)H.A * H.A + 3 * (size_t)H.A + H.Ar);
 }
 
+// blocked kernels (pbx_mid.cuh) for A <= 16 with the default M builder and scaling
+bool use_mid_path(const pbx_plan* p) { return p->H.A <= MID_AMAX && !p->jacobi && p->scale; }
+
+template <int AT>
+int launch_mid_at(pbx_plan* p, const double* R, long long n, const BeadOutputs& bo, double* out4, long long out_ld,
+                  cudaStream_t st) {
+    const HostTables& H = p->H;
+    const long long groups = n * ((H.P + MID_IB - 1) / MID_IB);
+    const size_t smem_b = MID_WARPS * mid_bead_warp_doubles(AT, H.Ar, H.N) * sizeof(double);
+    auto kb = pbx_mid_bead_kernel<AT>;
+    PBX_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    kb<<<(unsigned)((groups + MID_WARPS - 1) / MID_WARPS), MID_WARPS * 32, smem_b, st>>>(p->D, R, n, bo, H.has_quadratic ? 1 : 0);
+    PBX_CUDA(cudaGetLastError());
+    constexpr int spw = 32 / AT;
+    const unsigned grid = (unsigned)((n + (long long)MID_WARPS * spw - 1) / ((long long)MID_WARPS * spw));
+    const size_t smem_c = MID_WARPS * mid_chain_warp_doubles(AT) * sizeof(double);
+    if (p->pm) {
+        auto kc = pbx_mid_chain_kernel<AT, true>;
+        PBX_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        kc<<<grid, MID_WARPS * 32, smem_c, st>>>(p->D, bo.m_mat, bo.o_vib, bo.lr, n, out4, out4 + out_ld, out_ld);
+    } else {
+        auto kc = pbx_mid_chain_kernel<AT, false>;
+        PBX_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        kc<<<grid, MID_WARPS * 32, smem_c, st>>>(p->D, bo.m_mat, bo.o_vib, bo.lr, n, out4, out4 + out_ld, out_ld);
+    }
+    PBX_CUDA(cudaGetLastError());
+    p->launches += 2;
+    return PBX_OK;
+}
+
+int launch_mid(pbx_plan* p, const double* R, long long n, const BeadOutputs& bo, double* out4, long long out_ld,
+               cudaStream_t st) {
+    switch (p->H.A) {
+#define PBX_MID_CASE(A_) case A_: return launch_mid_at<A_>(p, R, n, bo, out4, out_ld, st);
+        PBX_MID_CASE(1) PBX_MID_CASE(2) PBX_MID_CASE(3) PBX_MID_CASE(4) PBX_MID_CASE(5) PBX_MID_CASE(6)
+        PBX_MID_CASE(7) PBX_MID_CASE(8) PBX_MID_CASE(9) PBX_MID_CASE(10) PBX_MID_CASE(11) PBX_MID_CASE(12)
+        PBX_MID_CASE(13) PBX_MID_CASE(14) PBX_MID_CASE(15) PBX_MID_CASE(16)
+#undef PBX_MID_CASE
+    }
+    return fail(PBX_ERR_UNSUPPORTED, "blocked kernels cover 1 <= A <= 16");
+}
+
 int launch_generic(pbx_plan* p, const double* R, long long n, double* out4, long long out_ld, cudaStream_t st) {
     // R: [n][N][P] device; intermediates in p->scratch (caller sized it)
     const HostTables& H = p->H;
@@ -216,6 +259,7 @@ int launch_generic(pbx_plan* p, const double* R, long long n, double* out4, long
     double* lr = o_vib + (size_t)3 * n * H.P * H.A;
     BeadOutputs bo{};
     bo.o_vib = o_vib; bo.lr = lr; bo.m_mat = m_mat; bo.n = n;
+    if (use_mid_path(p)) return launch_mid(p, R, n, bo, out4, out_ld, st);
     const long long items = n * H.P;
     const unsigned grid_b = (unsigned)((items + GEN_WARPS - 1) / GEN_WARPS);
     const size_t sm_b = GEN_WARPS * bead_warp_doubles(H.A, H.Ar, H.N) * sizeof(double);
@@ -240,10 +284,8 @@ int launch_generic(pbx_plan* p, const double* R, long long n, double* out4, long
 
 int launch_sample_coords(pbx_plan* p, unsigned long long seed, long long first, long long n, double* R, int* src,
                          cudaStream_t st) {
-    const int threads = 64;
-    const size_t sm = (size_t)2 * p->H.N * threads * sizeof(double);
-    PBX_CUDA(cudaFuncSetAttribute(pbx_sample_coords_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    pbx_sample_coords_kernel<<<(unsigned)((n + threads - 1) / threads), threads, sm, st>>>(p->D, seed, first, n, R, src);
+    const long long threads = n * ((p->H.N + 1) / 2);     // one thread per (sample, mode pair)
+    pbx_mid_sample_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p->D, seed, first, n, R, src);
     PBX_CUDA(cudaGetLastError());
     p->launches += 1;
     return PBX_OK;
@@ -301,8 +343,10 @@ int pbx_plan_create(const pbx_model* vib, const pbx_rho* rho, int32_t beads, dou
     DeviceGuard guard(device);
     if (!guard.ok) { delete p; return fail(PBX_ERR_CUDA, "cudaSetDevice failed"); }
     // shared-memory footprint of the generic kernels must fit an SM
-    const size_t sm_need = GEN_WARPS * std::max(bead_warp_doubles(p->H.A, p->H.Ar, p->H.N),
-                                                chain_warp_doubles(p->H.A, p->H.Ar)) * sizeof(double);
+    size_t sm_need = GEN_WARPS * std::max(bead_warp_doubles(p->H.A, p->H.Ar, p->H.N),
+                                          chain_warp_doubles(p->H.A, p->H.Ar)) * sizeof(double);
+    if (p->H.A <= MID_AMAX)
+        sm_need = std::max(sm_need, MID_WARPS * mid_bead_warp_doubles(p->H.A, p->H.Ar, p->H.N) * sizeof(double));
     if (sm_need > 200 * 1024) { delete p; return fail(PBX_ERR_UNSUPPORTED, "A too large for the generic kernels"); }
     rc = upload_tables(p);
     if (rc != PBX_OK) { pbx_plan_destroy(p); return rc; }

@@ -1,7 +1,7 @@
-// Generic (any A, N, A_rho) kernels: used for large-A models (BASELINE config c4: A=12, N=24) and
-// for the stage-by-stage introspection API.  Three steps through HBM scratch:
+// Generic (any A, N, A_rho) kernels: the universal fallback (A > 16, Jacobi M builder, unscaled
+// stage-by-stage introspection API); 1 <= A <= 16 normally runs on the blocked kernels of pbx_mid.cuh.  Three steps through HBM scratch:
 //
-//   coords  : R[x][n][p]                    (caller supplied, or pbx_sample_coords_kernel)
+//   coords  : R[x][n][p]                    (caller supplied, or pbx_mid_sample_kernel in pbx_mid.cuh)
 //   beads   : one WARP per (sample, bead):  O factors (log space), scale S, V, M = exp(-tau V)
 //             -> o_vib[3][x][P][A], lr[x][P][Ar], scale[x][P], v_mat / m_mat[x][P][A][A]
 //   chain   : one WARP per sample:          T_v <- (T_v M_p) diag(O_v[p]),  rho from the lr sums
@@ -40,47 +40,6 @@ constexpr int GEN_WARPS = 4;  // warps per CTA in the bead / chain kernels
 // shared memory (doubles) needed by one warp of the bead kernel
 __host__ __device__ inline size_t bead_warp_doubles(int A, int Ar, int N) {
     return 2 * (size_t)N + 3 * (size_t)A + Ar + 6 * (size_t)A * A;
-}
-
-// ---------------------------------------------------------------------------------------------
-// sampler only: thread per sample, beads in generation order, writes R[x][n][p] and the source
-// ---------------------------------------------------------------------------------------------
-__global__ void pbx_sample_coords_kernel(DevTables T, unsigned long long seed, long long first_sample,
-                                         long long n_samples, double* __restrict__ R, int* __restrict__ src_out) {
-    extern __shared__ double sm[];  // [2][N][blockDim]
-    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n_samples) return;
-    const int N = T.N, P = T.P, nt = blockDim.x, t = threadIdx.x;
-    double* y0 = sm;
-    double* yprev = sm + (size_t)N * nt;
-    const unsigned long long gidx = (unsigned long long)(first_sample + x);
-    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const uint4 rs = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, STREAM_SOURCE), key);
-    const double u = u01_half_open(rs.x, rs.y);
-    int src = 0;
-    for (int a = 0; a < T.Ar - 1; ++a) src += (u >= T.wcum[a]) ? 1 : 0;
-    if (src_out) src_out[x] = src;
-    const int half = (N + 1) / 2;
-    double* Rx = R + (size_t)x * N * P;
-    for (int j = 0; j < P; ++j) {
-        const double* tab = T.samp + (size_t)j * N * 3;
-        for (int h = 0; h < half; ++h) {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32),
-                                                     (uint32_t)(j * half + h), STREAM_NORMALS), key);
-            double z[2];
-            normal_pair(r, z[0], z[1]);
-            for (int w = 0; w < 2; ++w) {
-                const int n = 2 * h + w;
-                if (n < N) {
-                    double y = tab[n * 3 + 0] * z[w];
-                    if (j > 0) y = fma(tab[n * 3 + 1], yprev[n * nt + t], fma(tab[n * 3 + 2], y0[n * nt + t], y));
-                    if (j == 0) y0[n * nt + t] = y;
-                    yprev[n * nt + t] = y;
-                    Rx[(size_t)n * P + j] = y + T.d_rho[src * N + n];
-                }
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
