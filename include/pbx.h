@@ -163,6 +163,10 @@ int pbx_stats_dev(pbx_plan *plan, const double *out4_dev, int64_t n_samples, dou
 int pbx_stats_host(pbx_plan *plan, const double *out4_host, int64_t ld_host, int64_t n_samples, double *stats_host);
 int pbx_stats_last(pbx_plan *plan, double *stats_host);
 
+/* Self-test hook for the branch-free device math used by the kernels (pbx_device.cuh):
+ * kind 0 ln(x) for x in (0,1], 1 sqrt(x), 2 exp(x) for x <= 0, 3 sin(2 pi x), 4 cos(2 pi x) for x in [0,1). */
+int pbx_math_probe_dev(int32_t kind, const double *in_dev, double *out_dev, int64_t n, void *stream);
+
 /* Measured FP64 FMA throughput of the device in TFLOP/s (dependent-chain DFMA micro-kernel);
  * the roofline denominator used by bench.py. */
 int pbx_fp64_peak_tflops(int32_t device, double *tflops_out);

@@ -78,6 +78,7 @@ def lib():
         "pbx_stats_dev": (C.c_int, [vp, vp, i64, _dp, vp]),
         "pbx_stats_host": (C.c_int, [vp, vp, i64, i64, _dp]),
         "pbx_stats_last": (C.c_int, [vp, _dp]),
+        "pbx_math_probe_dev": (C.c_int, [i32, vp, vp, i64, vp]),
         "pbx_fp64_peak_tflops": (C.c_int, [i32, _dp]),
     }
     for name, (res, args) in sigs.items():
@@ -91,7 +92,7 @@ EXPORTED_SYMBOLS = ("pbx_abi_version", "pbx_last_error", "pbx_device_count", "pb
                     "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_launch_count", "pbx_sample_eval_dev",
                     "pbx_sample_eval_host", "pbx_eval_coords_dev", "pbx_eval_coords_host", "pbx_sample_coords_dev",
                     "pbx_eval_stages_dev", "pbx_chain_trace_dev", "pbx_block_sums_dev", "pbx_stats_dev", "pbx_stats_host",
-                    "pbx_stats_last", "pbx_fp64_peak_tflops")
+                    "pbx_stats_last", "pbx_math_probe_dev", "pbx_fp64_peak_tflops")
 
 
 def _check(rc):
@@ -271,6 +272,11 @@ class Plan:
 
 def device_count():
     return int(lib().pbx_device_count())
+
+
+def math_probe(kind, x, out, stream=None):
+    """device self-test of log_pos / sqrt_pos / exp_fast / sincos_2pi (kinds 0..4) on CUDA tensors"""
+    _check(lib().pbx_math_probe_dev(int(kind), _devptr(x), _devptr(out), int(x.numel()), _stream_handle(stream)))
 
 
 def fp64_peak_tflops(device=0):

@@ -42,7 +42,7 @@ struct DeviceGuard {
 };
 
 constexpr size_t kScratchTarget = (size_t)1 << 30;  // aim for <= 1 GiB of intermediates per chunk
-constexpr long long kFastCoordChunk = 1 << 16;      // samples per transposed-coordinate chunk
+constexpr long long kFastCoordChunk = 4 * 148 * 2 * 128;  // samples per transposed-coordinate chunk: 4 full waves of CTAs
 
 // ---- per-block sums ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -136,6 +136,18 @@ pbx_jackknife_kernel(const double* __restrict__ out4, long long ld, long long n,
         acc[0] += dE; acc[1] = fma(dE, dE, acc[1]); acc[2] += dC; acc[3] = fma(dC, dC, acc[3]);
     }
     cta_reduce_store<4>(acc, partials);
+}
+
+// ---- self-test of the branch-free device math (pbx_device.cuh) ------------------------------------------
+__global__ void pbx_math_probe_kernel(int kind, const double* __restrict__ in, double* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = in[i];
+    if (kind == 0) out[i] = log_pos(x);
+    else if (kind == 1) out[i] = sqrt_pos(x);
+    else if (kind == 2) out[i] = exp_fast(x);
+    else if (kind == 3) { double s, c; sincos_2pi(x, s, c); out[i] = s; }
+    else { double s, c; sincos_2pi(x, s, c); out[i] = c; }
 }
 
 // ---- FP64 peak probe: 8 independent dependent-FMA chains per thread ------------------------------
@@ -635,6 +647,13 @@ int pbx_stats_last(pbx_plan* p, double* stats_host) {
     PBX_NEED_DEVICE(p);
     if (p->io_samples < 2) return fail(PBX_ERR_ARG, "no device-resident results: call a *_host entry point first");
     return pbx_stats_dev(p, (const double*)p->io, p->io_samples, stats_host, p->own_stream);
+}
+
+int pbx_math_probe_dev(int32_t kind, const double* in_dev, double* out_dev, int64_t n, void* stream) {
+    if (!in_dev || !out_dev || n <= 0 || kind < 0 || kind > 4) return fail(PBX_ERR_ARG, "bad argument");
+    pbx_math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, in_dev, out_dev, n);
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
 }
 
 int pbx_fp64_peak_tflops(int32_t device, double* tflops_out) {

@@ -37,13 +37,104 @@ __device__ __forceinline__ double u01_half_open(uint32_t hi, uint32_t lo) {
     return (double)(bits >> 11) * 0x1.0p-53;
 }
 
+// ------------------------------------------------------------------------------------------
+// Branch-free FP64 elementary functions for the argument ranges this path needs.  The CUDA math
+// library versions carry slow-path branches (denormals, huge arguments, special values); a branch
+// ends the basic block, so ptxas cannot interleave independent evaluations -- in the sampler phase
+// that left one dependent chain at a time in flight (profiles/r01_summary.md).  Coefficients sit in
+// __constant__ memory: one LDCU.128 fetches two of them (an FP64 immediate costs two UMOVs).
+// Accuracy of each: a few ulp (checked against numpy in tests/test_gpu_parity.py::test_device_math).
+// ------------------------------------------------------------------------------------------
+static __constant__ double kLogC[8] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                1.479819860511658591e-01, 0.0};                       // fdlibm e_log.c Lg1..Lg7
+static __constant__ double kExpC[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
+                                 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
+static __constant__ double kSinC[8] = {-1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 362880, -1.0 / 39916800, 1.0 / 6227020800.0,
+                                -1.0 / 1307674368000.0, 0.0};
+static __constant__ double kCosC[8] = {-1.0 / 2, 1.0 / 24, -1.0 / 720, 1.0 / 40320, -1.0 / 3628800, 1.0 / 479001600,
+                                -1.0 / 87178291200.0, 1.0 / 20922789888000.0};
+constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
+
+// single MUFU instructions (the rounded intrinsics __frcp_rn / rsqrtf carry a slow-path branch)
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 1/d for d in [1, 4]: float seed (22 bits) + two Newton steps
+__device__ __forceinline__ double rcp_mid(double d) {
+    double y = (double)rcp_approx((float)d);
+    y = y * fma(-d, y, 2.0);
+    return y * fma(-d, y, 2.0);
+}
+
+// ln(u) for a normal, positive, finite u (here u in [2^-53, 1])
+__device__ __forceinline__ double log_pos(double u) {
+    int hi = __double2hiint(u);
+    const int lo = __double2loint(u);
+    int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;              // mantissa in [1, 2)
+    const bool big = hi >= 0x3ff6a09f;                // m >= sqrt(2) (top word of sqrt 2 is 0x3ff6a09e)
+    hi = big ? hi - 0x00100000 : hi;                  // m / 2
+    k += big ? 1 : 0;
+    const double m = __hiloint2double(hi, lo);
+    const double f = m - 1.0;
+    const double s = f * rcp_mid(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, kLogC[5], kLogC[3]), kLogC[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, kLogC[6], kLogC[4]), kLogC[2]), kLogC[0]);
+    const double R = t1 + t2, hfsq = 0.5 * f * f, dk = (double)k;
+    return fma(dk, kLn2Hi, -((hfsq - fma(s, hfsq + R, dk * kLn2Lo)) - f));
+}
+
+// sqrt(x) for x in [0, 1e6]; sqrt(0) returns ~1e-15 (x is -2 ln u with P(u == 1) = 2^-53)
+__device__ __forceinline__ double sqrt_pos(double x) {
+    const double xc = fmax(x, 1e-30);
+    double r = (double)rsqrt_approx((float)xc);
+    r = r * fma(-0.5 * xc, r * r, 1.5);
+    r = r * fma(-0.5 * xc, r * r, 1.5);
+    const double s = xc * r;
+    return fma(0.5 * r, fma(-s, s, xc), s);
+}
+
+// sin(2 pi u), cos(2 pi u) for u in [0, 1)
+__device__ __forceinline__ void sincos_2pi(double u, double& sn, double& cs) {
+    const double t = 4.0 * u;
+    const int q = __double2int_rn(t);                  // quarter turns, 0..4
+    const double x = (t - (double)q) * 1.5707963267948966;   // in [-pi/4, pi/4]
+    const double x2 = x * x;
+    double ps = kSinC[6];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) ps = fma(ps, x2, kSinC[i]);
+    double pc = kCosC[7];
+#pragma unroll
+    for (int i = 6; i >= 0; --i) pc = fma(pc, x2, kCosC[i]);
+    const double s0 = fma(x * x2, ps, x), c0 = fma(x2, pc, 1.0);
+    const bool swap = q & 1;
+    const double a = swap ? c0 : s0, b = swap ? s0 : c0;   // q=0: (s,c)  1: (c,-s)  2: (-s,-c)  3: (-c,s)
+    sn = (q & 2) ? -a : a;
+    cs = ((q + 1) & 2) ? -b : b;
+}
+
+// exp(x) for x <= 700 (arguments here are <= 0 up to rounding); exp(x < -708) = 0, exp(-inf) = 0
+__device__ __forceinline__ double exp_fast(double x) {
+    const double xc = fmax(x, -708.0);
+    const double dn = rint(xc * 1.4426950408889634);
+    double r = fma(-dn, kLn2Hi, xc);
+    r = fma(-dn, kLn2Lo, r);
+    double p = kExpC[13];
+#pragma unroll
+    for (int i = 12; i >= 0; --i) p = fma(p, r, kExpC[i]);
+    const double scale = __hiloint2double((__double2int_rn(dn) + 1023) << 20, 0);
+    return (x < -708.0) ? 0.0 : p * scale;
+}
+
 // two independent N(0,1) variates from one Philox block (Box-Muller, all FP64)
 __device__ __forceinline__ void normal_pair(uint4 r, double& z0, double& z1) {
     const double u1 = u01_open_low(r.x, r.y);
     const double u2 = u01_half_open(r.z, r.w);
-    const double rad = sqrt(-2.0 * log(u1));
+    const double rad = sqrt_pos(-2.0 * log_pos(u1));
     double s, c;
-    sincospi(2.0 * u2, &s, &c);
+    sincos_2pi(u2, s, c);
     z0 = rad * c;
     z1 = rad * s;
 }

@@ -32,6 +32,9 @@
 #ifndef PBX_SYNC_LOOP
 #define PBX_SYNC_LOOP 0      // 1: __syncthreads() per tile, keeps the CTA's warps in step (shared i-cache lines)
 #endif
+#ifndef PBX_UNROLL_H
+#define PBX_UNROLL_H 1       // 1: unroll the normal-pair loop of the sampler phase (independent chains interleave)
+#endif
 #ifndef PBX_DELTA_EXP
 #define PBX_DELTA_EXP 1      // 1: O(tau+-) = O(tau) * exp(delta), delta from analytic difference tables
 #endif
@@ -146,7 +149,7 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
     for (int a = 0; a < AR; ++a) lrho[a] += lr[a] - logS;
     double O[NV][A];
 #pragma unroll
-    for (int a = 0; a < A; ++a) O[0][a] = exp(lv[0][a] - logS);
+    for (int a = 0; a < A; ++a) O[0][a] = exp_fast(lv[0][a] - logS);
     if (PM) {
 #if PBX_DELTA_EXP
         double big = 0.0;
@@ -161,13 +164,13 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
         } else {   // huge delta_beta or far-out coordinates: full exponentials
 #pragma unroll
             for (int a = 0; a < A; ++a) {
-                O[1][a] = exp(lv[0][a] + lv[1][a] - logS);
-                O[2][a] = exp(lv[0][a] + lv[2][a] - logS);
+                O[1][a] = exp_fast(lv[0][a] + lv[1][a] - logS);
+                O[2][a] = exp_fast(lv[0][a] + lv[2][a] - logS);
             }
         }
 #else
 #pragma unroll
-        for (int a = 0; a < A; ++a) { O[1][a] = exp(lv[1][a] - logS); O[2][a] = exp(lv[2][a] - logS); }
+        for (int a = 0; a < A; ++a) { O[1][a] = exp_fast(lv[1][a] - logS); O[2][a] = exp_fast(lv[2][a] - logS); }
 #endif
     }
 
@@ -260,8 +263,12 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
                 return;
             }
             const double* tab = L.samp + (size_t)j * N * 3;
+#if PBX_UNROLL_H
+#pragma unroll
+#else
 #pragma unroll 1
-            for (int h = 0; h < (N + 1) / 2; ++h) {
+#endif
+            for (int h = 0; h < (N + 1) / 2; ++h) {   // branch-free body: unrolled pairs interleave
                 const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32),
                                                          (uint32_t)(j * ((N + 1) / 2) + h), STREAM_NORMALS), key);
                 double z[2];
@@ -281,8 +288,11 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
             }
         } else {
             const double* src = L.coords_t + (size_t)(j == P ? 0 : j) * L.ld + x;
-#pragma unroll 1
-            for (int n = 0; n < N; ++n) dst[n * nt] = __ldg(src + (size_t)n * P * L.ld);
+            double v[N];
+#pragma unroll
+            for (int n = 0; n < N; ++n) v[n] = __ldg(src + (size_t)n * P * L.ld);   // all loads in flight together
+#pragma unroll
+            for (int n = 0; n < N; ++n) dst[n * nt] = v[n];
         }
     };
 
@@ -303,9 +313,15 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
         __syncthreads();
 #endif
         // ---- phase S: beads t0+1 .. t0+TB into slots 1..TB (slot 0 holds bead t0)
+        if (MODE == MODE_SAMPLE) {
 #pragma unroll 1
-        for (int jj = 1; jj <= TB; ++jj)
-            if (t0 + jj <= P) put_bead(t0 + jj, jj);
+            for (int jj = 1; jj <= TB; ++jj)
+                if (t0 + jj <= P) put_bead(t0 + jj, jj);
+        } else {
+#pragma unroll
+            for (int jj = 1; jj <= TB; ++jj)
+                if (t0 + jj <= P) put_bead(t0 + jj, jj);
+        }
         // ---- phase E
 #pragma unroll 1
         for (int jj = 0; jj < TB; ++jj) {
@@ -326,7 +342,7 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
     if (!live) return;
     double rho = 0.0;
 #pragma unroll
-    for (int a = 0; a < AR; ++a) rho += exp(lrho[a]);
+    for (int a = 0; a < AR; ++a) rho += exp_fast(lrho[a]);
     L.out4[x] = rho;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {

@@ -792,6 +792,23 @@ def _compute_on_device(data, result, pm):
     return n
 
 
+def block_compute_gR(data, result):
+    """only g(R), NOT scaled by S, for blocks*block_size sampled points (pimc.py:1216-1247: data sets for
+    training ML models).  Runs on the unscaled generic kernels; saves the .npz like block_compute."""
+    import torch
+    n = int(data.blocks) * int(data.block_size)
+    assert 0 < n <= result.samples, "blocks*block_size must be in (0, samples]"
+    sampler = data.device_plan(pm=False)
+    plan = data.device_plan(pm=False, no_scaling=True)
+    with torch.cuda.device(plan.device):
+        R = torch.empty((n, data.modes, data.beads), dtype=torch.float64, device="cuda")
+        out = torch.empty((4, n), dtype=torch.float64, device="cuda")
+        sampler.sample_coords(data.seed, data.sample_offset, n, R)
+        plan.eval_coords(R, out)
+        result.scaled_g[:n] = out[1].cpu().numpy()
+    result.save_results(n)
+
+
 def block_compute(data, result):
     """numerator g and denominator rho for blocks*block_size sampled points; saves the .npz"""
     end = _compute_on_device(data, result, pm=False)

@@ -471,3 +471,53 @@ def test_sweep_statistics_and_thermo_files(cuda, tmp_path):
     assert thermo[(12, 250.0)]["E"] < thermo[(12, 300.0)]["E"]
     with pytest.raises(Exception, match="Invalid value for parameter method"):
         stats.statistical_analysis_of_pimc(FS, method="alpha")
+
+
+def test_block_compute_gR_is_unscaled(cuda, tmp_path):
+    """block_compute_gR (pimc.py:1216-1247): g without the S scaling, on the same Philox samples"""
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import file_structure, pimc, synthetic
+    FS = file_structure.FileStructure(tmp_path, 0, 0)
+    synthetic.write_data_set(FS, synthetic.coupled_model(2, 2, (0.02, 0.04), (0.1, 0.2), seed=3, linear=0.05))
+    FS.generate_model_hashes()
+    data = pimc.BoxData.from_FileStructure(FS)
+    data.samples, data.beads, data.temperature, data.block_size, data.blocks = 200, 12, 300.0, 100, 2
+    data.hash_vib, data.hash_rho, data.seed = FS.hash_vib, FS.hash_rho, 7
+    data.preprocess()
+    result = pimc.BoxResult(data=data)
+    result.path_root, result.id_job = FS.path_rho_results, 0
+    pimc.block_compute_gR(data, result)
+    data.draw_sample(slice(0, 100))
+    data.transform_sampled_coordinates(slice(0, 100))
+    R = np.ascontiguousarray(data.qTensor[:, 0])
+    tab = orc.precompute(orc.load_vibronic_json(FS.path_vib_model), orc.load_sampling_json(FS.path_rho_model), 12, 300.0)
+    _, g = orc.estimate_block(tab, R, pm=False, faithful=False, scale=False)
+    assert rel_err(result.scaled_g[:100], g) < RTOL
+    assert np.isnan(result.scaled_rho).all()
+    data.release()
+
+
+def test_device_math(cuda):
+    """the branch-free log / sqrt / exp / sincos of pbx_device.cuh against numpy, in units of ulp"""
+    rng = np.random.default_rng(0)
+    n = 1 << 20
+    cases = {
+        0: (np.concatenate([rng.random(n), 2.0 ** -rng.integers(1, 53, 4096), [1.0, 2.0 ** -53, 0.5, np.sqrt(0.5), 0.70710678118654757]]), np.log),
+        1: (np.concatenate([rng.random(n) * 80, rng.random(4096) * 1e-6, [75.0, 1.0, 4.0]]), np.sqrt),
+        2: (np.concatenate([-rng.random(n) * 60, -rng.random(4096) * 700, [0.0, -1e-300, -708.0, -745.0, -1e4, -np.inf, 1e-3]]), np.exp),
+        3: (np.concatenate([rng.random(n), [0.0, 0.25, 0.5, 0.75, 0.125, 1 - 2.0 ** -53]]), lambda u: np.sin(2 * np.pi * u)),
+        4: (np.concatenate([rng.random(n), [0.0, 0.25, 0.5, 0.75, 0.125, 1 - 2.0 ** -53]]), lambda u: np.cos(2 * np.pi * u)),
+    }
+    for kind, (x, fn) in cases.items():
+        xd = cuda.from_numpy(np.ascontiguousarray(x)).cuda()
+        out = cuda.empty_like(xd)
+        _cabi.math_probe(kind, xd, out)
+        got, want = out.cpu().numpy(), fn(x)
+        if kind in (3, 4):      # absolute: the argument reduction of numpy's 2*pi*u costs it an ulp of the angle
+            assert np.max(np.abs(got - want)) < 2e-15, kind
+        elif kind == 2:
+            tiny = want < 1e-300
+            assert np.all(got[tiny] <= 1e-300) and np.all(got[tiny] >= 0)
+            assert np.max(np.abs(got[~tiny] / want[~tiny] - 1)) < 1e-15, kind
+        else:
+            assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-15, kind
