@@ -45,20 +45,22 @@ template <int A, int N, int AR>
 struct FastTables {
     static constexpr int AA = A * (A + 1) / 2;
     static constexpr int NN = N * (N + 1) / 2;
-    double d_vib[A][N];
-    double d_rho[AR][N];
-    double hc[4][N];      // -0.5 * coth  (rows: vib tau, tau+, tau-, rho)
-    double cs[4][N];      // csch
-    double dhc[2][N];     // -0.5 * (coth(tau+-) - coth(tau))
-    double dcs[2][N];     // csch(tau+-) - csch(tau)
+    // harmonic exponent in half-angle form: l = logpref - 1/4 sum_n [tanh(x/2) (q+q')^2 + coth(x/2) (q-q')^2],
+    // x = tau*omega_n; with q = R - d the second term does not depend on the surface
+    double d2_vib[A][N];  // 2 * d
+    double d_rho[AR][N];  // d   (sampler shift)
+    double d2_rho[AR][N]; // 2 * d
+    double al[4][N];      // -1/4 tanh(x/2)  (rows: vib tau, tau+, tau-, rho)
+    double ga[4][N];      // -1/4 coth(x/2)
+    double dal[2][N];     // al(tau+-) - al(tau), formed analytically
+    double dga[2][N];     // ga(tau+-) - ga(tau)
     double lpref[3][A];
     double dlpref[2][A];
     double lpref_rho[AR];
     double wcum[AR];
-    double e_off[AA];
-    double l_off[N][AA];
+    double e_off[AA];     // the three coupling tables are pre-multiplied by -tau: the kernel builds X = -tau V directly
+    double l_off[N][AA];  // (M always uses tau, also for g+-: reference quirk Q2, pimc.py:1183)
     double q_pack[NN][AA];
-    double neg_tau;       // -tau (M always uses tau: reference quirk Q2, pimc.py:1183)
     int P;
     int n_rho_eval;
 };
@@ -94,24 +96,42 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
                                           double (&Tm)[PM ? 3 : 1][A][A], double (&lrho)[AR]) {
     constexpr int AA = A * (A + 1) / 2;
     constexpr int NV = PM ? 3 : 1;
-    // ---- harmonic factors, log space: l = logpref - 1/2 sum_n [coth (q^2+q'^2) - 2 csch q q']
+    // ---- harmonic factors, log space (half-angle form, see FastTables)
     double lv[NV][A], lr[AR];
+    double rs[N], w2[N];          // R_p + R_{p+1} and (R_p - R_{p+1})^2: surface independent
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, gr = 0.0;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const double w = Rc[n] - Rn[n];
+        rs[n] = Rc[n] + Rn[n];
+        w2[n] = w * w;
+        g0 = fma(T.ga[0][n], w2[n], g0);
+        if (PM) {
+#if PBX_DELTA_EXP
+            g1 = fma(T.dga[0][n], w2[n], g1);
+            g2 = fma(T.dga[1][n], w2[n], g2);
+#else
+            g1 = fma(T.ga[1][n], w2[n], g1);
+            g2 = fma(T.ga[2][n], w2[n], g2);
+#endif
+        }
+        if (!SHARE) gr = fma(T.ga[3][n], w2[n], gr);
+    }
 #pragma unroll
     for (int a = 0; a < A; ++a) {
-        double e0 = 0.0;
-        double e1 = 0.0, e2 = 0.0;   // PM: tau+ / tau- sums (differences from tau when PBX_DELTA_EXP)
+        double e0 = g0, e1 = g1, e2 = g2;
 #pragma unroll
         for (int n = 0; n < N; ++n) {
-            const double q = Rc[n] - T.d_vib[a][n], qn = Rn[n] - T.d_vib[a][n];
-            const double s2 = fma(q, q, qn * qn), pr = q * qn;
-            e0 = fma(T.hc[0][n], s2, fma(T.cs[0][n], pr, e0));
+            const double u = rs[n] - T.d2_vib[a][n];
+            const double u2 = u * u;
+            e0 = fma(T.al[0][n], u2, e0);
             if (PM) {
 #if PBX_DELTA_EXP
-                e1 = fma(T.dhc[0][n], s2, fma(T.dcs[0][n], pr, e1));
-                e2 = fma(T.dhc[1][n], s2, fma(T.dcs[1][n], pr, e2));
+                e1 = fma(T.dal[0][n], u2, e1);
+                e2 = fma(T.dal[1][n], u2, e2);
 #else
-                e1 = fma(T.hc[1][n], s2, fma(T.cs[1][n], pr, e1));
-                e2 = fma(T.hc[2][n], s2, fma(T.cs[2][n], pr, e2));
+                e1 = fma(T.al[1][n], u2, e1);
+                e2 = fma(T.al[2][n], u2, e2);
 #endif
             }
         }
@@ -130,13 +150,13 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
     if (!SHARE) {
 #pragma unroll
         for (int a = 0; a < AR; ++a) {
-            double acc = T.lpref_rho[a];
+            double acc = gr;
 #pragma unroll
             for (int n = 0; n < N; ++n) {
-                const double q = Rc[n] - T.d_rho[a][n], qn = Rn[n] - T.d_rho[a][n];
-                acc = fma(T.hc[3][n], fma(q, q, qn * qn), fma(T.cs[3][n], q * qn, acc));
+                const double u = rs[n] - T.d2_rho[a][n];
+                acc = fma(T.al[3][n], u * u, acc);
             }
-            lr[a] = (a < T.n_rho_eval) ? acc : -INFINITY;
+            lr[a] = (a < T.n_rho_eval) ? T.lpref_rho[a] + acc : -INFINITY;
         }
     }
     // S = max over both models' factors (pimc.py:1076-1084), kept as a logarithm
@@ -174,7 +194,7 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
 #endif
     }
 
-    // ---- X = -tau * V(R_p), packed symmetric
+    // ---- X = -tau * V(R_p), packed symmetric (the tables carry the factor -tau)
     double X[AA];
 #pragma unroll
     for (int k = 0; k < AA; ++k) X[k] = 0.0;
@@ -195,9 +215,6 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
 #pragma unroll
             for (int k = 0; k < AA; ++k) X[k] = fma(T.q_pack[pair_index(n, m, N)][k], rr, X[k]);
         }
-#pragma unroll
-    for (int k = 0; k < AA; ++k) X[k] *= T.neg_tau;
-
     double M[AA];
     if (JACOBI) sym_exp_jacobi<A>(X, M);
     else sym_expm<A>(X, M);
@@ -366,17 +383,17 @@ template <int A, int N, int AR>
 void fill_fast_tables(const HostTables& H, void* dst) {
     auto& T = *reinterpret_cast<FastTables<A, N, AR>*>(dst);
     constexpr int AA = A * (A + 1) / 2, NN = N * (N + 1) / 2;
-    for (int a = 0; a < A; ++a) for (int n = 0; n < N; ++n) T.d_vib[a][n] = H.d_vib[a * N + n];
-    for (int a = 0; a < AR; ++a) for (int n = 0; n < N; ++n) T.d_rho[a][n] = H.d_rho[a * N + n];
-    for (int v = 0; v < 4; ++v) for (int n = 0; n < N; ++n) { T.hc[v][n] = -0.5 * H.coth[v * N + n]; T.cs[v][n] = H.csch[v * N + n]; }
-    for (int v = 0; v < 2; ++v) for (int n = 0; n < N; ++n) { T.dhc[v][n] = -0.5 * H.dcoth[v * N + n]; T.dcs[v][n] = H.dcsch[v * N + n]; }
+    for (int a = 0; a < A; ++a) for (int n = 0; n < N; ++n) T.d2_vib[a][n] = 2.0 * H.d_vib[a * N + n];
+    for (int a = 0; a < AR; ++a) for (int n = 0; n < N; ++n) { T.d_rho[a][n] = H.d_rho[a * N + n]; T.d2_rho[a][n] = 2.0 * H.d_rho[a * N + n]; }
+    for (int v = 0; v < 4; ++v) for (int n = 0; n < N; ++n) { T.al[v][n] = -0.25 * H.tanh_half[v * N + n]; T.ga[v][n] = -0.25 * H.coth_half[v * N + n]; }
+    for (int v = 0; v < 2; ++v) for (int n = 0; n < N; ++n) { T.dal[v][n] = -0.25 * H.dtanh_half[v * N + n]; T.dga[v][n] = -0.25 * H.dcoth_half[v * N + n]; }
     for (int v = 0; v < 3; ++v) for (int a = 0; a < A; ++a) T.lpref[v][a] = H.logpref[v * A + a];
     for (int v = 0; v < 2; ++v) for (int a = 0; a < A; ++a) T.dlpref[v][a] = H.dlogpref[v * A + a];
     for (int a = 0; a < AR; ++a) { T.lpref_rho[a] = H.logpref_rho[a]; T.wcum[a] = H.wcum[a]; }
-    for (int k = 0; k < AA; ++k) T.e_off[k] = H.e_off[k];
-    for (int n = 0; n < N; ++n) for (int k = 0; k < AA; ++k) T.l_off[n][k] = H.l_off[(size_t)n * AA + k];
-    for (int q = 0; q < NN; ++q) for (int k = 0; k < AA; ++k) T.q_pack[q][k] = H.q_pack[(size_t)q * AA + k];
-    T.neg_tau = -H.tau[0];
+    const double mt = -H.tau[0];
+    for (int k = 0; k < AA; ++k) T.e_off[k] = mt * H.e_off[k];
+    for (int n = 0; n < N; ++n) for (int k = 0; k < AA; ++k) T.l_off[n][k] = mt * H.l_off[(size_t)n * AA + k];
+    for (int q = 0; q < NN; ++q) for (int k = 0; k < AA; ++k) T.q_pack[q][k] = mt * H.q_pack[(size_t)q * AA + k];
     T.P = H.P;
     T.n_rho_eval = H.n_rho_eval;
 }

@@ -36,6 +36,10 @@ struct HostTables {
     // differences of the tau+ / tau- tables from the tau ones, formed analytically (not by subtracting
     // rounded doubles): rows 0 = tau+ - tau, 1 = tau- - tau.  Used to get O(tau+-) = O(tau) * exp(delta).
     std::vector<double> dcoth, dcsch;     // [2][N]
+    // half-angle form of the harmonic exponent (no cancellation between the two terms):
+    //   coth(x)(q^2+q'^2) - 2 csch(x) q q' = 1/2 [ tanh(x/2) (q+q')^2 + coth(x/2) (q-q')^2 ]
+    std::vector<double> tanh_half, coth_half;     // [4][N] rows like coth/csch
+    std::vector<double> dtanh_half, dcoth_half;   // [2][N] analytic differences tau+- minus tau
     std::vector<double> dlogpref;         // [2][A]
     std::vector<double> logpref_rho;      // [Ar]
     std::vector<double> e_off;            // [AA]   diagonal entries zero
@@ -156,6 +160,7 @@ inline int build_tables(const pbx_model* vib, const pbx_rho* rho, int P, double 
     // ---- coth / csch / log prefactors (pimc.py:59-89)
     T.coth.assign(4 * N, 0.0); T.csch.assign(4 * N, 0.0);
     T.logpref.assign(3 * A, 0.0); T.logpref_rho.assign(Ar, 0.0);
+    T.tanh_half.assign(4 * N, 0.0); T.coth_half.assign(4 * N, 0.0);
     for (int v = 0; v < 4; ++v) {
         const long double t = (v < 3) ? T.tau[v] : T.tau[0];
         const double* om = (v < 3) ? vib->omega : rho->omega;
@@ -166,11 +171,17 @@ inline int build_tables(const pbx_model* vib, const pbx_rho* rho, int P, double 
             T.csch[v * N + n] = (double)(1.0L / std::sinh(x));
             half_log_csch += -0.5L * std::log(std::sinh(x));
         }
+        for (int n = 0; n < N; ++n) {
+            const long double hx = 0.5L * t * (long double)om[n];
+            T.tanh_half[v * N + n] = (double)std::tanh(hx);
+            T.coth_half[v * N + n] = (double)(1.0L / std::tanh(hx));
+        }
         if (v < 3) for (int a = 0; a < A; ++a) T.logpref[v * A + a] = (double)(-t * tilde[a] + half_log_csch);
         else for (int a = 0; a < Ar; ++a) T.logpref_rho[a] = (double)(-t * tilde_r[a] + half_log_csch);
     }
     // ---- analytic differences between the tau+/- and tau tables of the vibronic model
     T.dcoth.assign(2 * N, 0.0); T.dcsch.assign(2 * N, 0.0); T.dlogpref.assign(2 * A, 0.0);
+    T.dtanh_half.assign(2 * N, 0.0); T.dcoth_half.assign(2 * N, 0.0);
     for (int v = 1; v < 3; ++v) {
         const long double t0 = T.tau[0], tv = T.tau[v];
         long double half_dlog = 0.0L;
@@ -182,6 +193,10 @@ inline int build_tables(const pbx_model* vib, const pbx_rho* rho, int P, double 
             T.dcoth[(v - 1) * N + n] = (double)(std::sinh(a - b) / (sa * sb));
             T.dcsch[(v - 1) * N + n] = (double)(-dsinh / (sa * sb));
             half_dlog += -0.5L * std::log1p(dsinh / sa);   // -1/2 log(sinh b / sinh a)
+            // tanh(b/2) - tanh(a/2) = sinh((b-a)/2) / (cosh(a/2) cosh(b/2));  coth(b/2) - coth(a/2) = -sinh((b-a)/2) / (sinh(a/2) sinh(b/2))
+            const long double sh = std::sinh(0.5L * (b - a));
+            T.dtanh_half[(v - 1) * N + n] = (double)(sh / (std::cosh(0.5L * a) * std::cosh(0.5L * b)));
+            T.dcoth_half[(v - 1) * N + n] = (double)(-sh / (std::sinh(0.5L * a) * std::sinh(0.5L * b)));
         }
         for (int a = 0; a < A; ++a) T.dlogpref[(v - 1) * A + a] = (double)(-(tv - t0) * tilde[a] + half_dlog);
     }
