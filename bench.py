@@ -37,7 +37,7 @@ X_PER_GPU = 1_000_000
 BLOCK_SIZE = 10_000
 CPU_SAMPLES_PER_PROC = 8000   # bounded CPU sample: about 5-15 s per process
 CPU_BLOCK = 1000
-NCU_DRAM_BYTES_PER_LAUNCH = 111360   # from the committed ncu capture of the fused kernel, 1e6 samples per launch
+NCU_DRAM_BYTES_PER_LAUNCH = 69632   # from the committed ncu capture of the fused kernel, 1e6 samples per launch
 WORKLOAD = (f"c2: synthetic A={A} N={N} P={P} lin+quad coupling, T={T_KELVIN:.0f}K, PM path, "
             f"X={X_PER_GPU:.0e} samples/GPU/step in blocks of {BLOCK_SIZE}")
 
@@ -229,8 +229,7 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * X * P * e2e_steps / float(e2e_s.cpu())
     # the model tables travel to the device as the kernel's __grid_constant__ parameter on every launch
-    table_bytes = 8 * (sum(len(plan.table(t)) for t in ("d_vib", "d_rho", "coth", "csch", "logpref", "logpref_rho",
-                                                        "e_off", "l_off", "q_pack")) + 2 * (2 * N + A) + A + 1) + 64
+    table_bytes = plan.launch_param_bytes
 
     if rank == 0:
         flops = algorithmic_flops_per_sample(A, N, P, A)
@@ -251,7 +250,7 @@ def run_b200(args, rank, local_rank, world):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
-                                           "(profiles/r01_ncu_full_pbx_fast_kernel_v2.csv); the 32 MB of results stay in L2",
+                                           "(profiles/r01_ncu_full_pbx_fast_kernel_v3.csv); the 32 MB of results stay in L2",
                          "peak_source": "DFMA-chain probe in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                         "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
                          "kernel": "pbx_fast_kernel<4,6,4,SAMPLE,PM,expm>", "kernel_ms": kern_total_ms / args.steps,

@@ -111,6 +111,9 @@ int64_t pbx_plan_table(const pbx_plan *plan, const char *name, double *out, int6
 int pbx_plan_is_fast(const pbx_plan *plan);
 /* number of kernel launches issued through this plan so far */
 int64_t pbx_plan_launch_count(const pbx_plan *plan);
+/* bytes of kernel parameters (the model tables of the register-resident kernels travel this way) sent host->device
+ * with every estimator launch */
+int64_t pbx_plan_launch_param_bytes(const pbx_plan *plan);
 
 /* Fused sampler + estimator for global sample indices [first_sample, first_sample + n_samples).
  * Philox4x32-10 keyed by `seed`, counter = global sample index: results do not depend on how the

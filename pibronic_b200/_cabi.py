@@ -67,6 +67,7 @@ def lib():
         "pbx_plan_table": (i64, [vp, C.c_char_p, _dp, i64]),
         "pbx_plan_is_fast": (C.c_int, [vp]),
         "pbx_plan_launch_count": (i64, [vp]),
+        "pbx_plan_launch_param_bytes": (i64, [vp]),
         "pbx_sample_eval_dev": (C.c_int, [vp, u64, i64, i64, vp, vp]),
         "pbx_sample_eval_host": (C.c_int, [vp, u64, i64, i64, vp, i64, i64, vp]),
         "pbx_eval_coords_dev": (C.c_int, [vp, vp, i64, vp, vp]),
@@ -89,7 +90,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ("pbx_abi_version", "pbx_last_error", "pbx_device_count", "pbx_plan_create", "pbx_plan_destroy",
-                    "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_launch_count", "pbx_sample_eval_dev",
+                    "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_launch_count", "pbx_plan_launch_param_bytes", "pbx_sample_eval_dev",
                     "pbx_sample_eval_host", "pbx_eval_coords_dev", "pbx_eval_coords_host", "pbx_sample_coords_dev",
                     "pbx_eval_stages_dev", "pbx_chain_trace_dev", "pbx_block_sums_dev", "pbx_stats_dev", "pbx_stats_host",
                     "pbx_stats_last", "pbx_math_probe_dev", "pbx_fp64_peak_tflops")
@@ -176,6 +177,10 @@ class Plan:
     @property
     def launch_count(self):
         return int(lib().pbx_plan_launch_count(self._handle))
+
+    @property
+    def launch_param_bytes(self):
+        return int(lib().pbx_plan_launch_param_bytes(self._handle))
 
     def table(self, name):
         n = lib().pbx_plan_table(self._handle, name.encode(), None, 0)

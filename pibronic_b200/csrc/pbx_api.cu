@@ -403,6 +403,10 @@ int64_t pbx_plan_table(const pbx_plan* p, const char* name, double* out, int64_t
 
 int pbx_plan_is_fast(const pbx_plan* p) { return (p && p->fast) ? 1 : 0; }
 int64_t pbx_plan_launch_count(const pbx_plan* p) { return p ? p->launches : 0; }
+int64_t pbx_plan_launch_param_bytes(const pbx_plan* p) {
+    if (!p) return 0;
+    return p->fast ? (int64_t)(p->fast->table_bytes + sizeof(FastLaunch)) : (int64_t)sizeof(DevTables);
+}
 
 int pbx_sample_eval_dev(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n, double* out4, void* stream) {
     if (!p || !out4) return fail(PBX_ERR_ARG, "null argument");

@@ -18,6 +18,8 @@
 // Reference path reproduced per sample: /root/reference/pibronic/pimc/pimc.py:1420-1449
 // (block_compute_pm body) with the helpers at 1062-1213; SURVEY.md App. A.
 #pragma once
+#include <type_traits>
+
 #include "pbx_device.cuh"
 
 #ifndef PBX_BLOCK
@@ -91,9 +93,11 @@ __device__ __forceinline__ double exp_small(double d) {
 }
 
 // one bead of the estimator: updates the chained products Tm and the log-accumulators of rho
-template <int A, int N, int AR, bool PM, bool JACOBI, bool SHARE>
+// SAFE = false: O(tau+-) = O(tau) * exp_small(delta) unconditionally, `bad` records |delta| > 2^-5 (the caller then
+// redoes the sample with SAFE = true, full exponentials) -- keeps the hot loop free of a data dependent branch
+template <int A, int N, int AR, bool PM, bool JACOBI, bool SHARE, bool SAFE>
 __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const double (&Rc)[N], const double (&Rn)[N],
-                                          double (&Tm)[PM ? 3 : 1][A][A], double (&lrho)[AR]) {
+                                          double (&Tm)[PM ? 3 : 1][A][A], double (&lrho)[AR], bool& bad) {
     constexpr int AA = A * (A + 1) / 2;
     constexpr int NV = PM ? 3 : 1;
     // ---- harmonic factors, log space (half-angle form, see FastTables)
@@ -172,15 +176,15 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
     for (int a = 0; a < A; ++a) O[0][a] = exp_fast(lv[0][a] - logS);
     if (PM) {
 #if PBX_DELTA_EXP
-        double big = 0.0;
-#pragma unroll
-        for (int a = 0; a < A; ++a) big = fmax(big, fmax(fabs(lv[1][a]), fabs(lv[2][a])));
-        if (__all_sync(__activemask(), big <= 0.03125)) {
+        if (!SAFE) {
+            double big = 0.0;
 #pragma unroll
             for (int a = 0; a < A; ++a) {
+                big = fmax(big, fmax(fabs(lv[1][a]), fabs(lv[2][a])));
                 O[1][a] = O[0][a] * exp_small(lv[1][a]);
                 O[2][a] = O[0][a] * exp_small(lv[2][a]);
             }
+            bad = bad || !(big <= 0.03125);
         } else {   // huge delta_beta or far-out coordinates: full exponentials
 #pragma unroll
             for (int a = 0; a < A; ++a) {
@@ -313,61 +317,71 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
         }
     };
 
-    double Tm[NV][A][A];
+    double rho, tr[NV];
+    // the whole sample as a function of SAFE: state is rebuilt from the Philox counters, so a redo is exact
+    auto run_sample = [&](auto safe_tag) -> bool {
+        constexpr bool SAFE = decltype(safe_tag)::value;
+        bool bad = false;
+        double Tm[NV][A][A];
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
+        for (int v = 0; v < NV; ++v)
 #pragma unroll
-        for (int i = 0; i < A; ++i)
+            for (int i = 0; i < A; ++i)
 #pragma unroll
-            for (int j = 0; j < A; ++j) Tm[v][i][j] = (i == j) ? 1.0 : 0.0;
-    double lrho[AR];
+                for (int j = 0; j < A; ++j) Tm[v][i][j] = (i == j) ? 1.0 : 0.0;
+        double lrho[AR];
 #pragma unroll
-    for (int a = 0; a < AR; ++a) lrho[a] = 0.0;
+        for (int a = 0; a < AR; ++a) lrho[a] = 0.0;
 
-    put_bead(0, 0);
-    for (int t0 = 0; t0 < P; t0 += TB) {
-#if PBX_SYNC_LOOP
-        __syncthreads();
-#endif
-        // ---- phase S: beads t0+1 .. t0+TB into slots 1..TB (slot 0 holds bead t0)
-        if (MODE == MODE_SAMPLE) {
+        put_bead(0, 0);
+        for (int t0 = 0; t0 < P; t0 += TB) {
+            // ---- phase S: beads t0+1 .. t0+TB into slots 1..TB (slot 0 holds bead t0)
+            if (MODE == MODE_SAMPLE) {
 #pragma unroll 1
-            for (int jj = 1; jj <= TB; ++jj)
-                if (t0 + jj <= P) put_bead(t0 + jj, jj);
-        } else {
+                for (int jj = 1; jj <= TB; ++jj)
+                    if (t0 + jj <= P) put_bead(t0 + jj, jj);
+            } else {
 #pragma unroll
-            for (int jj = 1; jj <= TB; ++jj)
-                if (t0 + jj <= P) put_bead(t0 + jj, jj);
-        }
-        // ---- phase E
-#pragma unroll 1
-        for (int jj = 0; jj < TB; ++jj) {
-            if (t0 + jj >= P) break;
-            double Rc[N], Rn[N];
-#pragma unroll
-            for (int n = 0; n < N; ++n) {
-                Rc[n] = tile[(size_t)(jj * N + n) * nt];
-                Rn[n] = tile[(size_t)((jj + 1) * N + n) * nt];
+                for (int jj = 1; jj <= TB; ++jj)
+                    if (t0 + jj <= P) put_bead(t0 + jj, jj);
             }
-            bead_step<A, N, AR, PM, JACOBI, SHARE>(T, Rc, Rn, Tm, lrho);
+            // ---- phase E
+#pragma unroll 1
+            for (int jj = 0; jj < TB; ++jj) {
+                if (t0 + jj >= P) break;
+                double Rc[N], Rn[N];
+#pragma unroll
+                for (int n = 0; n < N; ++n) {
+                    Rc[n] = tile[(size_t)(jj * N + n) * nt];
+                    Rn[n] = tile[(size_t)((jj + 1) * N + n) * nt];
+                }
+                bead_step<A, N, AR, PM, JACOBI, SHARE, SAFE>(T, Rc, Rn, Tm, lrho, bad);
+            }
+            // bead t0+TB becomes slot 0 of the next tile
+#pragma unroll
+            for (int n = 0; n < N; ++n) tile[(size_t)n * nt] = tile[(size_t)(TB * N + n) * nt];
         }
-        // bead t0+TB becomes slot 0 of the next tile
+        rho = 0.0;
 #pragma unroll
-        for (int n = 0; n < N; ++n) tile[(size_t)n * nt] = tile[(size_t)(TB * N + n) * nt];
+        for (int a = 0; a < AR; ++a) rho += exp_fast(lrho[a]);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            tr[v] = 0.0;
+#pragma unroll
+            for (int i = 0; i < A; ++i) tr[v] += Tm[v][i][i];
+        }
+        return bad;
+    };
+    bool redo = run_sample(std::false_type{});
+    if (PM && PBX_DELTA_EXP) {
+        if (__any_sync(__activemask(), redo)) {     // cold path: never taken at delta_beta/beta ~ 5e-6
+            if (redo) run_sample(std::true_type{});
+        }
     }
-
     if (!live) return;
-    double rho = 0.0;
-#pragma unroll
-    for (int a = 0; a < AR; ++a) rho += exp_fast(lrho[a]);
     L.out4[x] = rho;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        double tr = 0.0;
-#pragma unroll
-        for (int i = 0; i < A; ++i) tr += Tm[v][i][i];
-        L.out4[(size_t)(1 + v) * L.out_ld + x] = tr;
-    }
+    for (int v = 0; v < NV; ++v) L.out4[(size_t)(1 + v) * L.out_ld + x] = tr[v];
 }
 
 // type-erased launcher stored in the plan

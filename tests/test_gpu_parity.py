@@ -521,3 +521,26 @@ def test_device_math(cuda):
             assert np.max(np.abs(got[~tiny] / want[~tiny] - 1)) < 1e-15, kind
         else:
             assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-15, kind
+
+
+@pytest.mark.parametrize("delta_beta", [0.5, 5.0])
+def test_large_delta_beta_takes_the_safe_path(cuda, delta_beta):
+    """delta_beta far above the default 2e-4: the tau+- factors are no longer a small correction of the tau ones,
+    the fast kernel must notice and redo those samples with full exponentials (same answer as the oracle)"""
+    from conftest import GoldenCase
+    from oracle import pimc_oracle as orc
+    for name in ("c2_4x6", "quad_3x4", "c5_altrho"):
+        case = GoldenCase(name)
+        beta = orc.beta_of(case.T)
+        plan = _cabi.Plan(case.vib["E"], case.vib["w"], case.vib["L"], case.vib["Q"], case.rho["E"], case.rho["w"],
+                          case.rho["L"], case.P, beta, delta_beta, flags=_cabi.FLAG_PM, device=0)
+        assert plan.is_fast
+        tab = orc.precompute(case.vib, case.rho, case.P, case.T, delta_beta=delta_beta)
+        got = plan.eval_coords_host(case.R)
+        want = oracle_eval(tab, case.R)
+        assert rel_err(got, want) < RTOL, name
+        n = 200
+        fused = plan.sample_eval_host(3, 0, n)
+        R, _ = drawn_coords(cuda, plan, 3, 0, n)
+        assert rel_err(fused, oracle_eval(tab, R)) < RTOL, name
+        plan.close()
