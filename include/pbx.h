@@ -64,7 +64,9 @@ enum {
     PBX_FLAG_EIG_JACOBI     = 1u << 3, /* M = U exp(-tau lambda) U^T by a Jacobi eigensolve (reference's  */
                                        /* formulation); default is a scaling-and-squaring exp(-tau V)      */
     PBX_FLAG_FORCE_GENERIC  = 1u << 4, /* never use the register-resident small-A kernels                 */
-    PBX_FLAG_NO_SCALING     = 1u << 5  /* skip the per-bead S scaling (golden test of the reference)       */
+    PBX_FLAG_NO_SCALING     = 1u << 5, /* skip the per-bead S scaling (golden test of the reference)       */
+    PBX_FLAG_NO_WARPSPEC    = 1u << 6  /* fused sampler+estimator on the one-role kernel instead of the        */
+                                       /* producer/consumer (warp-specialised) one; same results bit for bit  */
 };
 
 /* coupled (vibronic) model: pibronic `coupled_model.json` arrays as loaded by ModelClass.load_model */

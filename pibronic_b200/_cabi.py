@@ -20,6 +20,7 @@ FLAG_M_TAU_PM = 1 << 2
 FLAG_EIG_JACOBI = 1 << 3
 FLAG_FORCE_GENERIC = 1 << 4
 FLAG_NO_SCALING = 1 << 5
+FLAG_NO_WARPSPEC = 1 << 6
 NSUMS = 8
 SUM_NAMES = ("r", "r_plus", "r_minus", "r_sq", "d1", "d2", "d1_sq", "d2_sq")
 NSTATS = 10

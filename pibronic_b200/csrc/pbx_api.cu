@@ -418,6 +418,11 @@ int pbx_sample_eval_dev(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_
     if (p->fast) {
         FastLaunch L{};
         L.samp = p->D.samp; L.seed = seed; L.first_sample = first_sample; L.n_samples = n; L.out4 = out4; L.out_ld = n;
+        if (!p->jacobi && !(p->flags & PBX_FLAG_NO_WARPSPEC)) {   // producer/consumer warps (pbx_fast_ws.cuh)
+            PBX_CUDA(p->fast->launch_ws(p->fast_tables.data(), L, p->pm, p->H.rho_shares_vib, st));
+            p->launches += p->fast->ws_kernels(p->pm);
+            return PBX_OK;
+        }
         PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_SAMPLE, p->pm, p->jacobi, p->H.rho_shares_vib, st));
         p->launches += 1;
         return PBX_OK;

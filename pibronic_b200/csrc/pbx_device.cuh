@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "pbx_math_tables.h"
 #include "pbx_tables.hpp"
 
 namespace pbx {
@@ -45,9 +46,7 @@ __device__ __forceinline__ double u01_half_open(uint32_t hi, uint32_t lo) {
 // __constant__ memory: one LDCU.128 fetches two of them (an FP64 immediate costs two UMOVs).
 // Accuracy of each: a few ulp (checked against numpy in tests/test_gpu_parity.py::test_device_math).
 // ------------------------------------------------------------------------------------------
-static __constant__ double kLogC[8] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
-                                2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
-                                1.479819860511658591e-01, 0.0};                       // fdlibm e_log.c Lg1..Lg7
+static __constant__ double kLog1pC[6] = {-1.0 / 2, 1.0 / 3, -1.0 / 4, 1.0 / 5, -1.0 / 6, 1.0 / 7};   // log1p(t) = t + t^2 Q(t)
 static __constant__ double kExpC[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
                                  1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
 static __constant__ double kSinC[8] = {-1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 362880, -1.0 / 39916800, 1.0 / 6227020800.0,
@@ -56,41 +55,35 @@ static __constant__ double kCosC[8] = {-1.0 / 2, 1.0 / 24, -1.0 / 720, 1.0 / 403
                                 -1.0 / 87178291200.0, 1.0 / 20922789888000.0};
 constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
 
-// single MUFU instructions (the rounded intrinsics __frcp_rn / rsqrtf carry a slow-path branch)
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// single MUFU instruction (the rounded intrinsic rsqrtf carries a slow-path branch)
 __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// 1/d for d in [1, 4]: float seed (22 bits) + two Newton steps
-__device__ __forceinline__ double rcp_mid(double d) {
-    double y = (double)rcp_approx((float)d);
-    y = y * fma(-d, y, 2.0);
-    return y * fma(-d, y, 2.0);
-}
-
-// ln(u) for a normal, positive, finite u (here u in [2^-53, 1])
+// ln(u) for a normal, positive, finite u (here u in [2^-53, 1]): u = 2^k m with m in [0.75, 1.5),
+// ln m = -ln(rc) + log1p(m rc - 1) with rc ~ 1/m from a 97-entry table (pbx_math_tables.h; the pair of u's
+// lane is one 16-byte L1 load), |m rc - 1| <= 1/192 so a degree-7 series is exact to 7e-20.  The centre of
+// the cell around m = 1 is exactly 1: ln u keeps full RELATIVE accuracy for u -> 1.  11 FP64 instructions.
 __device__ __forceinline__ double log_pos(double u) {
-    int hi = __double2hiint(u);
-    const int lo = __double2loint(u);
-    int k = (hi >> 20) - 1023;
-    hi = (hi & 0x000fffff) | 0x3ff00000;              // mantissa in [1, 2)
-    const bool big = hi >= 0x3ff6a09f;                // m >= sqrt(2) (top word of sqrt 2 is 0x3ff6a09e)
-    hi = big ? hi - 0x00100000 : hi;                  // m / 2
-    k += big ? 1 : 0;
-    const double m = __hiloint2double(hi, lo);
-    const double f = m - 1.0;
-    const double s = f * rcp_mid(2.0 + f);
-    const double z = s * s, w = z * z;
-    const double t1 = w * fma(w, fma(w, kLogC[5], kLogC[3]), kLogC[1]);
-    const double t2 = z * fma(w, fma(w, fma(w, kLogC[6], kLogC[4]), kLogC[2]), kLogC[0]);
-    const double R = t1 + t2, hfsq = 0.5 * f * f, dk = (double)k;
-    return fma(dk, kLn2Hi, -((hfsq - fma(s, hfsq + R, dk * kLn2Lo)) - f));
+    const int hi = __double2hiint(u), lo = __double2loint(u);
+    const int frac = hi & 0x000fffff;
+    const bool big = frac >= 0x00080000;                       // mantissa >= 1.5: use m / 2 in [0.75, 1)
+    const int k = (hi >> 20) - 1023 + (big ? 1 : 0);
+    const int idx = big ? ((frac + 0x2000) >> 14) - 32 : ((frac + 0x1000) >> 13) + 32;   // round(128 m) - 96
+    const double m = __hiloint2double(frac | (big ? 0x3fe00000 : 0x3ff00000), lo);
+    const double2 tb = __ldg(reinterpret_cast<const double2*>(kLogTab) + idx);
+    const double t = fma(m, tb.x, -1.0);
+    double q = kLog1pC[5];
+#pragma unroll
+    for (int i = 4; i >= 0; --i) q = fma(q, t, kLog1pC[i]);
+    const double l1p = fma(t * t, q, t);
+    const double dk = (double)k;
+    return fma(dk, kLn2Hi, tb.y) + fma(dk, kLn2Lo, l1p);      // dk * kLn2Hi is exact (32-bit kLn2Hi)
 }
 
-// sqrt(x) for x in [0, 1e6]; sqrt(0) returns ~1e-15 (x is -2 ln u with P(u == 1) = 2^-53)
+// sqrt(x) for x in [0, 1e6]; sqrt(0) returns ~1e-15 (x is -2 ln u with P(u == 1) = 2^-53).
+// MUFU seed (22 bits) -> one Newton step on 1/sqrt (44 bits) -> one coupled step on sqrt (88 bits before rounding)
 __device__ __forceinline__ double sqrt_pos(double x) {
     const double xc = fmax(x, 1e-30);
     double r = (double)rsqrt_approx((float)xc);
-    r = r * fma(-0.5 * xc, r * r, 1.5);
     r = r * fma(-0.5 * xc, r * r, 1.5);
     const double s = xc * r;
     return fma(0.5 * r, fma(-s, s, xc), s);
@@ -115,17 +108,23 @@ __device__ __forceinline__ void sincos_2pi(double u, double& sn, double& cs) {
     cs = ((q + 1) & 2) ? -b : b;
 }
 
-// exp(x) for x <= 700 (arguments here are <= 0 up to rounding); exp(x < -708) = 0, exp(-inf) = 0
+// exp(x) for x <= 700 (arguments here are <= 0 up to rounding); exp(x < -708) = 0, exp(-inf) = 0.
+// x = (32 k + j) ln2/32 + r, |r| <= ln2/64: exp(x) = 2^k 2^(j/32) p(r) with a 32-entry table and a degree-6
+// polynomial (remainder 3.5e-18); the integer n = 32 k + j is read off the low word of x*32/ln2 + 1.5*2^52, and
+// 2^k is an integer add on the exponent field (the product stays normal for x >= -708).  10 FP64 instructions.
 __device__ __forceinline__ double exp_fast(double x) {
-    const double xc = fmax(x, -708.0);
-    const double dn = rint(xc * 1.4426950408889634);
-    double r = fma(-dn, kLn2Hi, xc);
-    r = fma(-dn, kLn2Lo, r);
-    double p = kExpC[13];
+    constexpr double kMagic = 6755399441055744.0;              // 1.5 * 2^52
+    const double t = fma(x, 46.166241308446828, kMagic);       // 32 / ln 2
+    const int n = __double2loint(t);
+    const double dn = t - kMagic;
+    double r = fma(dn, -kLn2Hi * 0.03125, x);
+    r = fma(dn, -kLn2Lo * 0.03125, r);
+    double p = kExpC[6];
 #pragma unroll
-    for (int i = 12; i >= 0; --i) p = fma(p, r, kExpC[i]);
-    const double scale = __hiloint2double((__double2int_rn(dn) + 1023) << 20, 0);
-    return (x < -708.0) ? 0.0 : p * scale;
+    for (int i = 5; i >= 0; --i) p = fma(p, r, kExpC[i]);
+    const double v = p * __ldg(kExp2Tab + (n & 31));
+    const double scaled = __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
+    return (x >= -708.0) ? scaled : 0.0;                       // also x = -inf / NaN garbage -> 0
 }
 
 // two independent N(0,1) variates from one Philox block (Box-Muller, all FP64)
@@ -168,9 +167,23 @@ __device__ __forceinline__ void sym_mul(const double (&X)[A * (A + 1) / 2], cons
         }
 }
 
+// Number of squarings s for exp(X) = (T12(X / 2^s))^(2^s): the smallest s >= 0 with ||X||_1 / 2^s < theta.
+// theta = 1/3 bounds the truncation error of the degree-12 Taylor polynomial by
+// theta^13/13! * e^theta = 1.4e-16 (in the 2-norm, which the 1-norm overestimates), i.e. half an ulp of the O(1) entries of M;
+// theta = 1/4 (PBX_EXPM_THETA_INV 4) gives 2.4e-18 but costs a squaring whenever 1/4 <= ||X|| < 1/3 -- on the c2
+// workload that is 3 % of the beads but 68 % of the WARPS (the loop runs to the largest s of the 32 lanes).
+#ifndef PBX_EXPM_THETA_INV
+#define PBX_EXPM_THETA_INV 3
+#endif
+__device__ __forceinline__ int expm_squarings(double norm) {
+    // y = norm / theta = m * 2^e with m in [0.5, 1)  ->  s = max(0, e)
+    int s = ((__double2hiint(norm * (double)PBX_EXPM_THETA_INV) >> 20) & 0x7ff) - 1022;
+    return s < 0 ? 0 : (s > 60 ? 60 : s);
+}
+
 // M = exp(X) for symmetric X by scaling and squaring with a degree-12 Taylor polynomial evaluated
 // Paterson-Stockmeyer style (X^2, X^3, X^4 + two Horner steps in X^4 = 5 products) and
-// s = max(0, ceil(log2(||X||_1 / 0.25))) squarings.  Truncation error <= 0.25^13/13! = 2.4e-18.
+// s = expm_squarings(||X||_1) squarings.
 template <int A>
 __device__ __forceinline__ void sym_expm(double (&X)[A * (A + 1) / 2], double (&M)[A * (A + 1) / 2]) {
     constexpr int AA = A * (A + 1) / 2;
@@ -182,9 +195,7 @@ __device__ __forceinline__ void sym_expm(double (&X)[A * (A + 1) / 2], double (&
         for (int j = 0; j < A; ++j) row += fabs(X[sym(i, j)]);
         norm = fmax(norm, row);
     }
-    // norm = m * 2^e with m in [0.5, 1): scaling by 2^-(e+2) brings the norm below 0.25
-    int s = ((__double2hiint(norm) >> 20) & 0x7ff) - 1022 + 2;
-    s = s < 0 ? 0 : (s > 60 ? 60 : s);
+    const int s = expm_squarings(norm);
     const double scale = __hiloint2double((1023 - s) << 20, 0);
 #pragma unroll
     for (int k = 0; k < AA; ++k) X[k] *= scale;

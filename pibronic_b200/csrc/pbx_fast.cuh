@@ -31,9 +31,6 @@
 #ifndef PBX_TILE
 #define PBX_TILE 8           // beads per tile
 #endif
-#ifndef PBX_SYNC_LOOP
-#define PBX_SYNC_LOOP 0      // 1: __syncthreads() per tile, keeps the CTA's warps in step (shared i-cache lines)
-#endif
 #ifndef PBX_UNROLL_H
 #define PBX_UNROLL_H 1       // 1: unroll the normal-pair loop of the sampler phase (independent chains interleave)
 #endif
@@ -78,22 +75,26 @@ struct FastLaunch {
     long long out_ld;
 };
 
-enum { MODE_SAMPLE = 0, MODE_COORDS = 1 };
+// MODE_REDO: MODE_SAMPLE restricted to the samples the warp-specialised kernel (pbx_fast_ws.cuh) flagged with
+// rho = NaN (|log O(tau+-) - log O(tau)| beyond the short-series range); evaluated with full exponentials
+enum { MODE_SAMPLE = 0, MODE_COORDS = 1, MODE_REDO = 2 };
 
-// exp(d) for |d| <= 2^-5 by a degree-7 Taylor polynomial (remainder < 2.3e-17)
+// exp(d) for |d| <= 2^-8 by a degree-5 Taylor polynomial (remainder < 4.9e-18)
 __device__ __forceinline__ double exp_small(double d) {
-    double p = 1.0 / 5040;
-    p = fma(p, d, 1.0 / 720);
-    p = fma(p, d, 1.0 / 120);
+    double p = 1.0 / 120;
     p = fma(p, d, 1.0 / 24);
     p = fma(p, d, 1.0 / 6);
     p = fma(p, d, 0.5);
     p = fma(p, d, 1.0);
     return fma(p, d, 1.0);
 }
+// |d| >= 2^-8, NaN or inf, decided on the exponent field (integer pipe: the FP64 pipe is the bottleneck)
+__device__ __forceinline__ bool exp_small_out_of_range(double d) {
+    return (__double2hiint(d) & 0x7fffffff) >= 0x3f700000;
+}
 
 // one bead of the estimator: updates the chained products Tm and the log-accumulators of rho
-// SAFE = false: O(tau+-) = O(tau) * exp_small(delta) unconditionally, `bad` records |delta| > 2^-5 (the caller then
+// SAFE = false: O(tau+-) = O(tau) * exp_small(delta) unconditionally, `bad` records |delta| >= 2^-8 (the caller then
 // redoes the sample with SAFE = true, full exponentials) -- keeps the hot loop free of a data dependent branch
 template <int A, int N, int AR, bool PM, bool JACOBI, bool SHARE, bool SAFE>
 __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const double (&Rc)[N], const double (&Rn)[N],
@@ -177,14 +178,12 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
     if (PM) {
 #if PBX_DELTA_EXP
         if (!SAFE) {
-            double big = 0.0;
 #pragma unroll
             for (int a = 0; a < A; ++a) {
-                big = fmax(big, fmax(fabs(lv[1][a]), fabs(lv[2][a])));
+                bad = bad || exp_small_out_of_range(lv[1][a]) || exp_small_out_of_range(lv[2][a]);
                 O[1][a] = O[0][a] * exp_small(lv[1][a]);
                 O[2][a] = O[0][a] * exp_small(lv[2][a]);
             }
-            bad = bad || !(big <= 0.03125);
         } else {   // huge delta_beta or far-out coordinates: full exponentials
 #pragma unroll
             for (int a = 0; a < A; ++a) {
@@ -261,9 +260,12 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
     double* yprev = y0 + (size_t)N * nt;                     // [N]
     double* dsrc = yprev + (size_t)N * nt;                   // [N] shift of the mixture component drawn
 
+    if (MODE == MODE_REDO) {
+        if (!live || !isnan(L.out4[x])) return;   // no block-wide barrier in this kernel: threads may leave
+    }
     const unsigned long long gidx = (unsigned long long)(L.first_sample + x);
     const uint2 key = make_uint2((uint32_t)L.seed, (uint32_t)(L.seed >> 32));
-    if (MODE == MODE_SAMPLE) {
+    if (MODE != MODE_COORDS) {
         const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, STREAM_SOURCE), key);
         const int src = pick_source<AR>(u01_half_open(r.x, r.y), T.wcum);
 #pragma unroll
@@ -277,7 +279,7 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
     // coordinates of bead j (j == P closes the ring: bead 0 again) into tile slot `slot`
     auto put_bead = [&](int j, int slot) {
         double* dst = tile + (size_t)slot * N * nt;
-        if (MODE == MODE_SAMPLE) {
+        if (MODE != MODE_COORDS) {
             if (j == P) {
 #pragma unroll 1
                 for (int n = 0; n < N; ++n) dst[n * nt] = y0[n * nt] + dsrc[n * nt];
@@ -336,7 +338,7 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
         put_bead(0, 0);
         for (int t0 = 0; t0 < P; t0 += TB) {
             // ---- phase S: beads t0+1 .. t0+TB into slots 1..TB (slot 0 holds bead t0)
-            if (MODE == MODE_SAMPLE) {
+            if (MODE != MODE_COORDS) {
 #pragma unroll 1
                 for (int jj = 1; jj <= TB; ++jj)
                     if (t0 + jj <= P) put_bead(t0 + jj, jj);
@@ -372,10 +374,14 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
         }
         return bad;
     };
-    bool redo = run_sample(std::false_type{});
-    if (PM && PBX_DELTA_EXP) {
-        if (__any_sync(__activemask(), redo)) {     // cold path: never taken at delta_beta/beta ~ 5e-6
-            if (redo) run_sample(std::true_type{});
+    if constexpr (MODE == MODE_REDO) {
+        run_sample(std::true_type{});
+    } else {
+        bool redo = run_sample(std::false_type{});
+        if (PM && PBX_DELTA_EXP) {
+            if (__any_sync(__activemask(), redo)) {     // cold path: never taken at delta_beta/beta ~ 5e-6
+                if (redo) run_sample(std::true_type{});
+            }
         }
     }
     if (!live) return;
@@ -391,6 +397,9 @@ struct FastKernelEntry {
     void (*fill)(const HostTables&, void* dst);
     cudaError_t (*launch)(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share,
                           cudaStream_t stream);
+    // warp-specialised sampler + estimator (pbx_fast_ws.cuh; scaling-and-squaring M only); enqueues `ws_kernels(pm)` kernels
+    cudaError_t (*launch_ws)(const void* tables, const FastLaunch& L, bool pm, bool share, cudaStream_t stream);
+    int (*ws_kernels)(bool pm);
 };
 
 template <int A, int N, int AR>
@@ -446,11 +455,6 @@ cudaError_t launch_fast(const void* tables, const FastLaunch& L, int mode, bool 
     if (mode == MODE_SAMPLE) { PBX_DISPATCH(MODE_SAMPLE) }
     PBX_DISPATCH(MODE_COORDS)
 #undef PBX_DISPATCH
-}
-
-template <int A, int N, int AR>
-constexpr FastKernelEntry make_entry() {
-    return FastKernelEntry{A, N, AR, sizeof(FastTables<A, N, AR>), &fill_fast_tables<A, N, AR>, &launch_fast<A, N, AR>};
 }
 
 // defined in pbx_fast_registry.cu

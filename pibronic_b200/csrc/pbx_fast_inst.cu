@@ -1,7 +1,7 @@
 // Instantiation registry of the register-resident small-A kernels (pbx_fast.cuh).
 // One translation unit per (A, N, A_rho) shape so that `make -j` compiles them in parallel:
 // this file is compiled once per shape with -DPBX_A=.. -DPBX_N=.. -DPBX_AR=..
-#include "pbx_fast.cuh"
+#include "pbx_fast_ws.cuh"
 
 namespace pbx {
 #define PBX_CAT_(a, b, c, d) a##b##_##c##_##d

@@ -144,8 +144,7 @@ __device__ __forceinline__ const double* warp_expm_at(double* X, double* W0, dou
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) norm = fmax(norm, __shfl_xor_sync(0xffffffffu, norm, o));
-    int s = ((__double2hiint(norm) >> 20) & 0x7ff) - 1022 + 2;
-    s = s < 0 ? 0 : (s > 60 ? 60 : s);
+    const int s = expm_squarings(norm);
     const double scale = __hiloint2double((1023 - s) << 20, 0);
     for (int e = lane; e < AA2; e += 32) X[e] *= scale;
     __syncwarp();

@@ -154,6 +154,23 @@ def test_fused_kernel_equals_sampler_then_estimator(cuda, case, variant):
     plan.close()
 
 
+@pytest.mark.parametrize("pm", [True, False])
+def test_warp_specialised_kernel_is_bit_identical(cuda, case, pm):
+    """producer/consumer kernel (default for the fused call) == one-role kernel, same Philox counters and arithmetic;
+    n = 700 leaves a partly filled CTA, first_sample != 0 exercises the 64-bit counter"""
+    base = (_cabi.FLAG_PM if pm else 0) | _cabi.QUIRK_RHO_TRUNC
+    ws, one = case.plan(base), case.plan(base | _cabi.FLAG_NO_WARPSPEC)
+    if not ws.is_fast:
+        pytest.skip("shape runs on the generic kernels")
+    rows = 4 if pm else 2
+    for n, first in ((700, (1 << 33) + 5), (1, 0), (256, 256)):
+        a = ws.sample_eval_host(99, first, n, out4=np.full((rows, n), np.nan))
+        b = one.sample_eval_host(99, first, n, out4=np.full((rows, n), np.nan))
+        assert np.all(np.isfinite(a)) and np.array_equal(a, b), (n, first)
+    ws.close()
+    one.close()
+
+
 def test_results_do_not_depend_on_how_the_index_range_is_split(cuda, case):
     plan = case.plan()
     n, seed = 1000, 77
@@ -502,7 +519,8 @@ def test_device_math(cuda):
     rng = np.random.default_rng(0)
     n = 1 << 20
     cases = {
-        0: (np.concatenate([rng.random(n), 2.0 ** -rng.integers(1, 53, 4096), [1.0, 2.0 ** -53, 0.5, np.sqrt(0.5), 0.70710678118654757]]), np.log),
+        0: (np.concatenate([rng.random(n), 2.0 ** -rng.integers(1, 53, 4096), [1.0, 2.0 ** -53, 0.5, np.sqrt(0.5), 0.70710678118654757,
+                            1 - 2.0 ** -53, 1 - 2.0 ** -30, 0.75, np.nextafter(0.75, 0), 0.375, np.nextafter(0.5, 0)]]), np.log),
         1: (np.concatenate([rng.random(n) * 80, rng.random(4096) * 1e-6, [75.0, 1.0, 4.0]]), np.sqrt),
         2: (np.concatenate([-rng.random(n) * 60, -rng.random(4096) * 700, [0.0, -1e-300, -708.0, -745.0, -1e4, -np.inf, 1e-3]]), np.exp),
         3: (np.concatenate([rng.random(n), [0.0, 0.25, 0.5, 0.75, 0.125, 1 - 2.0 ** -53]]), lambda u: np.sin(2 * np.pi * u)),

@@ -37,15 +37,18 @@ def time_plan(plan, X, reps=3):
 
 
 def main():
-    X = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
+    pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+    X = int(float(pos[0])) if pos else 1_000_000
     model = synthetic.model_c2()
     if "--quick" in sys.argv:
         import os
-        plan = make_plan(model, 64, 300.0, _cabi.FLAG_PM)
-        ms, out = time_plan(plan, X, reps=5)
-        o = out.cpu().numpy()
-        print(f"{os.environ.get('PBX_LIB', 'default'):40s} c2 expm PM X={X} {ms:8.3f} ms  {X * 64 / ms * 1e3:.3e} samples*beads/s "
-              f"<g/rho>={(o[1] / o[0]).mean():.5f}")
+        for name, extra in (("warp-specialised", 0), ("one-role", _cabi.FLAG_NO_WARPSPEC)):
+            plan = make_plan(model, 64, 300.0, _cabi.FLAG_PM | extra)
+            ms, out = time_plan(plan, X, reps=5)
+            o = out.cpu().numpy()
+            print(f"{os.path.basename(os.environ.get('PBX_LIB', 'default')):24s} {name:17s} c2 expm PM X={X} {ms:8.3f} ms  "
+                  f"{X * 64 / ms * 1e3:.3e} samples*beads/s <g/rho>={(o[1] / o[0]).mean():.5f}")
+            plan.close()
         return
     print("fp64 peak (DFMA probe): %.2f TFLOP/s" % _cabi.fp64_peak_tflops(0))
     for name, flags in (("expm", _cabi.FLAG_PM), ("jacobi", _cabi.FLAG_PM | _cabi.FLAG_EIG_JACOBI),
