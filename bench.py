@@ -5,12 +5,14 @@
 
 Workload (config c2 of BASELINE.json): synthetic A=4 surfaces, N=6 modes, P=64 beads, linear +
 quadratic coupling, T=300 K, X = 1e6 samples per GPU per step in blocks of 1e4, PM path
-(rho, g, g+, g-).  One step = one fused sampler+estimator launch over X samples + the per-block
-sums (+ one NCCL all-reduce of the block sums when N > 1).  Weak scaling: every GPU does X samples.
+(rho, g, g+, g-).  One step = one fused sampler+estimator launch over X samples (warp-specialised
+kernel + its redo pass) + the per-block sums (+ one NCCL all-reduce of the block sums when N > 1).
+Weak scaling: every GPU does X samples.
 
 value   : device-resident throughput, CUDA events around each step, max over ranks.
-e2e     : the same step through the host-buffer C ABI call (pbx_sample_eval_host): results and
-          block sums are copied device->host into pinned memory inside the timed region.
+e2e     : the same step through the host-buffer C ABI call (pbx_sample_eval_host) with pinned host
+          buffers: the 32 MB of results reach the host inside the timed region (the kernel stores them
+          into the mapped buffer as it goes; the block sums are copied after it).
 roofline: FP64 vector pipe.  achieved = algorithmic flop/sample (with the
           sampler term counted for the O(P) recurrence actually used) x samples/s;
           peak = DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 entry).
@@ -37,7 +39,7 @@ X_PER_GPU = 1_000_000
 BLOCK_SIZE = 10_000
 CPU_SAMPLES_PER_PROC = 8000   # bounded CPU sample: about 5-15 s per process
 CPU_BLOCK = 1000
-NCU_DRAM_BYTES_PER_LAUNCH = 69632   # from the committed ncu capture of the fused kernel, 1e6 samples per launch
+NCU_DRAM_BYTES_PER_LAUNCH = 79616 + 427264   # from the committed ncu capture of the fused kernel, 1e6 samples per launch
 WORKLOAD = (f"c2: synthetic A={A} N={N} P={P} lin+quad coupling, T={T_KELVIN:.0f}K, PM path, "
             f"X={X_PER_GPU:.0e} samples/GPU/step in blocks of {BLOCK_SIZE}")
 
@@ -250,10 +252,11 @@ def run_b200(args, rank, local_rank, world):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
-                                           "(profiles/r01_ncu_full_pbx_fast_kernel_v3.csv); the 32 MB of results stay in L2",
+                                           "(profiles/r01_ncu_full_pbx_fast_ws_kernel.csv); the 32 MB of results stay in L2",
                          "peak_source": "DFMA-chain probe in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                         "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
-                         "kernel": "pbx_fast_kernel<4,6,4,SAMPLE,PM,expm>", "kernel_ms": kern_total_ms / args.steps,
+                         "kernel": "pbx_fast_ws_kernel<4,6,4,PM,shared-rho> (+ its MODE_REDO pass, ~10 us, inside kernel_ms)",
+                         "kernel_ms": kern_total_ms / args.steps,
                          "flop_per_sample": flops, "algorithmic_bytes_per_sample": 32},
             "cpu_baseline": {"value": cpu_rate, "unit": "samples*beads/s", "cores": cpu_procs, "kind": "port",
                              "sample": f"{cpu_procs} processes x {CPU_SAMPLES_PER_PROC} samples, numpy port of "
@@ -261,7 +264,7 @@ def run_b200(args, rank, local_rank, world):
                                        f"{cpu_dt if cpu_dt is None else round(cpu_dt, 2)} s"},
             "e2e": {"value": e2e_value, "unit": "samples*beads/s", "h2d_bytes_per_step": table_bytes,
                     "d2h_bytes_per_step": 4 * X * 8 + blocks * _cabi.NSUMS * 8, "steps": e2e_steps,
-                    "call": "pbx_sample_eval_host (pinned host buffers)"},
+                    "call": "pbx_sample_eval_host (pinned, mapped host buffers: results written by the kernel, sums copied)"},
             "gpu_launches": int(gpu_launches),
             "clocks": clock_info,
             "check": {"mean_g_over_rho": float(ratio.mean()), "stderr": float(ratio.std() / np.sqrt(X)),
@@ -276,7 +279,7 @@ def run_b200(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -408,16 +408,17 @@ int64_t pbx_plan_launch_param_bytes(const pbx_plan* p) {
     return p->fast ? (int64_t)(p->fast->table_bytes + sizeof(FastLaunch)) : (int64_t)sizeof(DevTables);
 }
 
-int pbx_sample_eval_dev(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n, double* out4, void* stream) {
-    if (!p || !out4) return fail(PBX_ERR_ARG, "null argument");
-    if (n <= 0) return PBX_OK;
-    if (first_sample < 0) return fail(PBX_ERR_ARG, "first_sample < 0");
-    PBX_NEED_DEVICE(p);
-    DeviceGuard guard(p->device);
-    cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+
+namespace {
+// fused sampler + estimator into out4 [4][n] (device); `mirror` (nullable, register-resident kernels only) is a
+// device-accessible HOST copy [4][mirror_ld] the kernel writes as well
+int sample_eval_impl(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n, double* out4, double* mirror,
+                     int64_t mirror_ld, cudaStream_t st) {
     if (p->fast) {
         FastLaunch L{};
         L.samp = p->D.samp; L.seed = seed; L.first_sample = first_sample; L.n_samples = n; L.out4 = out4; L.out_ld = n;
+        L.mirror = mirror; L.mirror_ld = mirror_ld;
         if (!p->jacobi && !(p->flags & PBX_FLAG_NO_WARPSPEC)) {   // producer/consumer warps (pbx_fast_ws.cuh)
             PBX_CUDA(p->fast->launch_ws(p->fast_tables.data(), L, p->pm, p->H.rho_shares_vib, st));
             p->launches += p->fast->ws_kernels(p->pm);
@@ -440,6 +441,29 @@ int pbx_sample_eval_dev(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_
         if (rc != PBX_OK) return rc;
     }
     return PBX_OK;
+}
+
+// device-visible alias of a host pointer if the range is pinned and mapped (cudaHostAlloc / cudaHostRegister), else null
+double* mapped_alias(double* host, size_t bytes) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    cudaPointerAttributes end{};
+    if (cudaPointerGetAttributes(&end, (char*)host + bytes - 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (end.type != cudaMemoryTypeHost || !end.devicePointer) return nullptr;
+    return (double*)at.devicePointer;
+}
+}  // namespace
+
+extern "C" {
+
+int pbx_sample_eval_dev(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n, double* out4, void* stream) {
+    if (!p || !out4) return fail(PBX_ERR_ARG, "null argument");
+    if (n <= 0) return PBX_OK;
+    if (first_sample < 0) return fail(PBX_ERR_ARG, "first_sample < 0");
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    return sample_eval_impl(p, seed, first_sample, n, out4, nullptr, 0, (cudaStream_t)stream);
 }
 
 int pbx_eval_coords_dev(pbx_plan* p, const double* R, int64_t n, double* out4, void* stream) {
@@ -550,15 +574,19 @@ int pbx_sample_eval_host(pbx_plan* p, uint64_t seed, int64_t first_sample, int64
     double* out_dev = (double*)p->io;
     double* sums_dev = out_dev + (size_t)4 * n;
     p->io_samples = n;
-    rc = pbx_sample_eval_dev(p, seed, first_sample, n, out_dev, p->own_stream);
+    if (first_sample < 0) return fail(PBX_ERR_ARG, "first_sample < 0");
+    const size_t rows = p->pm ? 4 : 2;
+    // pinned + mapped host buffer and a register-resident kernel: the kernel writes the host rows itself
+    double* mirror = p->fast ? mapped_alias(out4_host, ((rows - 1) * (size_t)ld_host + (size_t)n) * sizeof(double)) : nullptr;
+    rc = sample_eval_impl(p, seed, first_sample, n, out_dev, mirror, ld_host, p->own_stream);
     if (rc != PBX_OK) return rc;
     if (sums_host) {
         rc = pbx_block_sums_dev(p, out_dev, n, block_size, sums_dev, p->own_stream);
         if (rc != PBX_OK) return rc;
     }
-    const size_t rows = p->pm ? 4 : 2;
-    PBX_CUDA(cudaMemcpy2DAsync(out4_host, ld_host * sizeof(double), out_dev, n * sizeof(double), n * sizeof(double), rows,
-                               cudaMemcpyDeviceToHost, p->own_stream));
+    if (!mirror)
+        PBX_CUDA(cudaMemcpy2DAsync(out4_host, ld_host * sizeof(double), out_dev, n * sizeof(double), n * sizeof(double), rows,
+                                   cudaMemcpyDeviceToHost, p->own_stream));
     if (sums_host)
         PBX_CUDA(cudaMemcpyAsync(sums_host, sums_dev, (size_t)blocks * PBX_NSUMS * sizeof(double), cudaMemcpyDeviceToHost,
                                  p->own_stream));

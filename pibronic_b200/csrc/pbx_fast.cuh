@@ -73,6 +73,8 @@ struct FastLaunch {
     long long n_samples;
     double* out4;            // [4][out_ld]
     long long out_ld;
+    double* mirror;          // optional second copy of the results, [4][mirror_ld]: mapped pinned HOST memory written
+    long long mirror_ld;     // straight from the kernel (posted PCIe writes overlap the compute; no D2H pass afterwards)
 };
 
 // MODE_REDO: MODE_SAMPLE restricted to the samples the warp-specialised kernel (pbx_fast_ws.cuh) flagged with
@@ -388,6 +390,11 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
     L.out4[x] = rho;
 #pragma unroll
     for (int v = 0; v < NV; ++v) L.out4[(size_t)(1 + v) * L.out_ld + x] = tr[v];
+    if (L.mirror) {
+        L.mirror[x] = rho;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) L.mirror[(size_t)(1 + v) * L.mirror_ld + x] = tr[v];
+    }
 }
 
 // type-erased launcher stored in the plan

@@ -231,13 +231,16 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
     double rho = 0.0;
 #pragma unroll
     for (int a = 0; a < AR; ++a) rho += exp_fast(lrho[a]);
-    L.out4[x] = bad ? __longlong_as_double(0x7ff8000000000000LL) : rho;
+    if (bad) rho = __longlong_as_double(0x7ff8000000000000LL);     // NaN: picked up by the MODE_REDO launch
+    L.out4[x] = rho;
+    if (L.mirror) L.mirror[x] = rho;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         double tr = 0.0;
 #pragma unroll
         for (int i = 0; i < A; ++i) tr += Tm[v][i][i];
         L.out4[(size_t)(1 + v) * L.out_ld + x] = tr;
+        if (L.mirror) L.mirror[(size_t)(1 + v) * L.mirror_ld + x] = tr;
     }
 }
 

@@ -171,6 +171,20 @@ def test_warp_specialised_kernel_is_bit_identical(cuda, case, pm):
     one.close()
 
 
+def test_pinned_host_buffer_is_written_by_the_kernel_itself(cuda, case):
+    """a pinned (mapped) host buffer takes the zero-copy route -- the kernel stores the host rows directly --
+    a pageable one the staged D2H copy; same bytes either way, also with a row stride and on the large-delta redo path"""
+    plan = case.plan()
+    n, ld = 777, 1000
+    pageable = plan.sample_eval_host(5, 10, n)
+    pinned = cuda.full((4, ld), float("nan"), dtype=cuda.float64).pin_memory().numpy()
+    got, sums = plan.sample_eval_host(5, 10, n, out4=pinned[:, :n], block_size=100)
+    assert np.array_equal(got, pageable) and np.isnan(pinned[:, n:]).all()
+    _, sums_pageable = plan.sample_eval_host(5, 10, n, block_size=100)
+    assert np.array_equal(sums, sums_pageable)
+    plan.close()
+
+
 def test_results_do_not_depend_on_how_the_index_range_is_split(cuda, case):
     plan = case.plan()
     n, seed = 1000, 77
