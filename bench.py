@@ -15,7 +15,8 @@ e2e     : the same step through the host-buffer C ABI call (pbx_sample_eval_host
           into the mapped buffer as it goes; the block sums are copied after it).
 roofline: FP64 vector pipe.  achieved = algorithmic flop/sample (with the
           sampler term counted for the O(P) recurrence actually used) x samples/s;
-          peak = DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+          peak = FP64 FMA rate measured in this run, the larger of a vector DFMA-chain probe and an
+          FP64 tensor (DMMA) probe (MEASURED_PEAKS.json has no FP64 entry).
 cpu_baseline / --impl reference: the numpy port of the reference's block loop (oracle/, "port")
           on a bounded sample, one process per host core with single-threaded BLAS.
 """
@@ -182,7 +183,9 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    peak = _cabi.fp64_peak_tflops(local_rank)
+    peak_vector = _cabi.fp64_peak_tflops(local_rank, 0)
+    peak_tensor = _cabi.fp64_peak_tflops(local_rank, 1)
+    peak = max(peak_vector, peak_tensor)   # one set of FP64 units behind both paths: the higher reading is the roofline
     for k in range(args.warmup):
         step(k)
     barrier()
@@ -253,8 +256,11 @@ def run_b200(args, rank, local_rank, world):
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
                                            "(profiles/r01_ncu_full_pbx_fast_ws_kernel.csv); the 32 MB of results stay in L2",
-                         "peak_source": "DFMA-chain probe in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                                        "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
+                         "peak_source": "measured in this run (MEASURED_PEAKS.json has no FP64 entry): the larger of a vector "
+                                        "DFMA-chain probe and an FP64 tensor (mma.sync m8n8k4) probe, which share the FP64 units "
+                                        "on B200; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
+                         "peak_vector_dfma": peak_vector, "peak_tensor_dmma": peak_tensor,
+                         "frac_of_vector_peak": achieved / peak_vector,
                          "kernel": "pbx_fast_ws_kernel<4,6,4,PM,shared-rho> (+ its MODE_REDO pass, ~10 us, inside kernel_ms)",
                          "kernel_ms": kern_total_ms / args.steps,
                          "flop_per_sample": flops, "algorithmic_bytes_per_sample": 32},

@@ -175,6 +175,9 @@ int pbx_math_probe_dev(int32_t kind, const double *in_dev, double *out_dev, int6
 /* Measured FP64 FMA throughput of the device in TFLOP/s (dependent-chain DFMA micro-kernel);
  * the roofline denominator used by bench.py. */
 int pbx_fp64_peak_tflops(int32_t device, double *tflops_out);
+/* kind 0: the vector DFMA probe above; 1: the same through the FP64 tensor path (mma.sync m8n8k4, which shares the
+ * FP64 units with the vector pipe on B200 but reaches a higher fraction of them); 2: the larger of the two. */
+int pbx_fp64_peak_tflops_kind(int32_t device, int32_t kind, double *tflops_out);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,7 @@ def lib():
         "pbx_stats_last": (C.c_int, [vp, _dp]),
         "pbx_math_probe_dev": (C.c_int, [i32, vp, vp, i64, vp]),
         "pbx_fp64_peak_tflops": (C.c_int, [i32, _dp]),
+        "pbx_fp64_peak_tflops_kind": (C.c_int, [i32, i32, _dp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -94,7 +95,7 @@ EXPORTED_SYMBOLS = ("pbx_abi_version", "pbx_last_error", "pbx_device_count", "pb
                     "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_launch_count", "pbx_plan_launch_param_bytes", "pbx_sample_eval_dev",
                     "pbx_sample_eval_host", "pbx_eval_coords_dev", "pbx_eval_coords_host", "pbx_sample_coords_dev",
                     "pbx_eval_stages_dev", "pbx_chain_trace_dev", "pbx_block_sums_dev", "pbx_stats_dev", "pbx_stats_host",
-                    "pbx_stats_last", "pbx_math_probe_dev", "pbx_fp64_peak_tflops")
+                    "pbx_stats_last", "pbx_math_probe_dev", "pbx_fp64_peak_tflops", "pbx_fp64_peak_tflops_kind")
 
 
 def _check(rc):
@@ -285,7 +286,8 @@ def math_probe(kind, x, out, stream=None):
     _check(lib().pbx_math_probe_dev(int(kind), _devptr(x), _devptr(out), int(x.numel()), _stream_handle(stream)))
 
 
-def fp64_peak_tflops(device=0):
+def fp64_peak_tflops(device=0, kind=0):
+    """measured FP64 FMA rate: kind 0 vector DFMA chains, 1 tensor DMMA (mma.sync m8n8k4), 2 the larger of the two"""
     out = C.c_double(0.0)
-    _check(lib().pbx_fp64_peak_tflops(int(device), C.byref(out)))
+    _check(lib().pbx_fp64_peak_tflops_kind(int(device), int(kind), C.byref(out)))
     return out.value

@@ -164,6 +164,24 @@ __global__ void __launch_bounds__(256) pbx_dfma_probe_kernel(double* out, int it
     if (s == 123.456) out[0] = s;  // never true; keeps the loop alive
 }
 
+// same measurement through the FP64 tensor path: 8 independent m8n8k4 accumulator tiles per warp.  On B200 the two share
+// the FP64 units (tools/microbench/dmma_mix.cu: mixed loops never exceed the DMMA-only rate), DMMA merely reaches
+// them with fewer operand reads: 37.2 vs 34.0 TFLOP/s
+__global__ void __launch_bounds__(256) pbx_dmma_probe_kernel(double* out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k][0] = threadIdx.x * 1e-9; c[k][1] = k; }
+    for (int i = 0; i < iters; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    if (s == 123.456) out[0] = s;
+}
+
 }  // namespace
 
 struct pbx_plan {
@@ -693,7 +711,10 @@ int pbx_math_probe_dev(int32_t kind, const double* in_dev, double* out_dev, int6
     return PBX_OK;
 }
 
-int pbx_fp64_peak_tflops(int32_t device, double* tflops_out) {
+}  // extern "C"
+
+namespace {
+int fp64_peak(int32_t device, int which, double* tflops_out) {
     if (!tflops_out) return fail(PBX_ERR_ARG, "null argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -709,19 +730,33 @@ int pbx_fp64_peak_tflops(int32_t device, double* tflops_out) {
     cudaEvent_t e0, e1;
     PBX_CUDA(cudaEventCreate(&e0)); PBX_CUDA(cudaEventCreate(&e1));
     double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
-        PBX_CUDA(cudaEventRecord(e0));
-        pbx_dfma_probe_kernel<<<grid, 256>>>(dummy, iters, 0.999999, 1e-7);
-        PBX_CUDA(cudaEventRecord(e1));
-        PBX_CUDA(cudaEventSynchronize(e1));
-        float ms = 0;
-        PBX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = 2.0 * 8.0 * iters * 256.0 * grid;
-        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    for (int kind = 0; kind < 2; ++kind) {
+        if (kind != which && which != 2) continue;
+        for (int rep = 0; rep < 5; ++rep) {
+            PBX_CUDA(cudaEventRecord(e0));
+            if (kind == 0) pbx_dfma_probe_kernel<<<grid, 256>>>(dummy, iters, 0.999999, 1e-7);
+            else pbx_dmma_probe_kernel<<<grid, 256>>>(dummy, iters / 8, 0.999999, 1e-7);
+            PBX_CUDA(cudaEventRecord(e1));
+            PBX_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            PBX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            // per thread and iteration: 8 FMAs (vector) or 8 tiles x 256 FMAs / 32 lanes (tensor), over iters/8 iterations
+            const double flops = 2.0 * 8.0 * iters * 256.0 * grid;
+            if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dummy);
     *tflops_out = best;
     return PBX_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int pbx_fp64_peak_tflops(int32_t device, double* tflops_out) { return fp64_peak(device, 0, tflops_out); }
+int pbx_fp64_peak_tflops_kind(int32_t device, int32_t kind, double* tflops_out) {
+    if (kind < 0 || kind > 2) return fail(PBX_ERR_ARG, "kind must be 0 (vector DFMA), 1 (tensor DMMA) or 2 (the larger)");
+    return fp64_peak(device, kind, tflops_out);
 }
 
 }  // extern "C"
