@@ -60,3 +60,40 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch
+
+
+class PaperFamily:
+    """BASELINE configs[2] (c3): every model of the reference's examples/paper_1.5025058 with each of its alternate
+    sampling distributions, coordinates and outputs of the UNMODIFIED reference at P=128, T=250 and 350 K
+    (tests/golden/c3_paper.npz, made by tests/golden/make_c3_paper.py)"""
+
+    def __init__(self, root):
+        from oracle import pimc_oracle as orc
+        self.data = np.load(join(GOLDEN, "c3_paper.npz"))
+        self.names = [str(n) for n in self.data["names"]]
+        self.P = int(self.data["P"])
+        self.root, self.orc = str(root), orc
+        self._models = {}
+
+    def run(self, name):
+        """(vib, rho, T, R, expected[4][X]) of one run; `exact(name)` has the 80-bit values"""
+        key = name.rsplit("_T", 1)[0]
+        if key not in self._models:
+            paths = []
+            for kind in ("vib", "rho"):
+                path = join(self.root, f"{key}_{kind}.json")
+                with open(path, "w", encoding="UTF8") as fh:
+                    fh.write(str(self.data[f"{name}/{kind}"]))
+                paths.append(path)
+            self._models[key] = (self.orc.load_vibronic_json(paths[0]), self.orc.load_sampling_json(paths[1]))
+        vib, rho = self._models[key]
+        return vib, rho, float(name.rsplit("_T", 1)[1]), np.ascontiguousarray(self.data[name + "/R"]), self.data[name + "/out"]
+
+    def exact(self, name):
+        """the four numbers of every sample evaluated in 80-bit arithmetic (tests/golden/extended_precision.py)"""
+        return self.data[name + "/exact"]
+
+
+@pytest.fixture(scope="session")
+def paper_family(tmp_path_factory):
+    return PaperFamily(tmp_path_factory.mktemp("c3_paper"))
