@@ -190,6 +190,8 @@ struct pbx_plan {
     uint32_t flags = 0;
     bool pm = false, jacobi = false, scale = true;
     double* dev_tables = nullptr;
+    int* dev_int_tables = nullptr;
+    double* dmma_tables = nullptr;
     DevTables D{};
     const FastKernelEntry* fast = nullptr;
     std::vector<unsigned char> fast_tables;
@@ -234,6 +236,47 @@ int upload_tables(pbx_plan* p) {
     return PBX_OK;
 }
 
+// coupling tables in mma.sync.m8n8k4.f64 fragment order (see DevTables)
+int upload_dmma_tables(pbx_plan* p) {
+    const HostTables& H = p->H;
+    const int N = H.N, AA = H.AA, ONE = N;       // row N of the coordinate tile holds ones
+    std::vector<int> fa, fb;
+    std::vector<const double*> coef;
+    if (H.has_quadratic)
+        for (int n = 0; n < N; ++n)
+            for (int m = n; m < N; ++m) { fa.push_back(n); fb.push_back(m); coef.push_back(&H.q_pack[(size_t)pair_index(n, m, N) * AA]); }
+    for (int n = 0; n < N; ++n) { fa.push_back(n); fb.push_back(ONE); coef.push_back(&H.l_off[(size_t)n * AA]); }
+    fa.push_back(ONE); fb.push_back(ONE); coef.push_back(H.e_off.data());
+    const int K = (int)fa.size(), KS = (K + 3) / 4, NT = (AA + 7) / 8;
+    std::vector<double> q((size_t)KS * NT * 32, 0.0);
+    for (int ks = 0; ks < KS; ++ks)
+        for (int j = 0; j < NT; ++j)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int f = 4 * ks + lane % 4, k = 8 * j + lane / 4;
+                if (f < K && k < AA) q[((size_t)ks * NT + j) * 32 + lane] = coef[f][k];
+            }
+    std::vector<int> ints((size_t)4 * KS + 8 * NT);
+    for (int f = 0; f < 4 * KS; ++f) ints[f] = f < K ? (fa[f] | (fb[f] << 16)) : (ONE | (ONE << 16));
+    for (int k = 0; k < 8 * NT; ++k) {
+        int v = -1;
+        if (k < AA) {
+            int i = 0;
+            while (tri(i + 1, 0) <= k) ++i;
+            v = (i << 16) | (k - tri(i, 0));
+        }
+        ints[(size_t)4 * KS + k] = v;
+    }
+    double* dq = nullptr;
+    PBX_CUDA(cudaMalloc((void**)&dq, q.size() * sizeof(double)));
+    p->dmma_tables = dq;
+    PBX_CUDA(cudaMemcpy(dq, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
+    PBX_CUDA(cudaMalloc((void**)&p->dev_int_tables, ints.size() * sizeof(int)));
+    PBX_CUDA(cudaMemcpy(p->dev_int_tables, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice));
+    p->D.q_dmma = dq; p->D.feat = p->dev_int_tables; p->D.tri_ij = p->dev_int_tables + 4 * KS;
+    p->D.KS = KS; p->D.NT = NT;
+    return PBX_OK;
+}
+
 // doubles of intermediates per sample on the generic path (coords excluded)
 size_t generic_doubles_per_sample(const HostTables& H) {
     return (size_t)H.P * ((size_t)H.A * H.A + 3 * (size_t)H.A + H.Ar);
@@ -250,7 +293,7 @@ int launch_mid_at(pbx_plan* p, const double* R, long long n, const BeadOutputs& 
     const size_t smem_b = MID_WARPS * mid_bead_warp_doubles(AT, H.Ar, H.N) * sizeof(double);
     auto kb = pbx_mid_bead_kernel<AT>;
     PBX_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    kb<<<(unsigned)((groups + MID_WARPS - 1) / MID_WARPS), MID_WARPS * 32, smem_b, st>>>(p->D, R, n, bo, H.has_quadratic ? 1 : 0);
+    kb<<<(unsigned)((groups + MID_WARPS - 1) / MID_WARPS), MID_WARPS * 32, smem_b, st>>>(p->D, R, n, bo);
     PBX_CUDA(cudaGetLastError());
     constexpr int spw = 32 / AT;
     const unsigned grid = (unsigned)((n + (long long)MID_WARPS * spw - 1) / ((long long)MID_WARPS * spw));
@@ -380,6 +423,10 @@ int pbx_plan_create(const pbx_model* vib, const pbx_rho* rho, int32_t beads, dou
     if (sm_need > 200 * 1024) { delete p; return fail(PBX_ERR_UNSUPPORTED, "A too large for the generic kernels"); }
     rc = upload_tables(p);
     if (rc != PBX_OK) { pbx_plan_destroy(p); return rc; }
+    if (p->H.A <= MID_AMAX) {
+        rc = upload_dmma_tables(p);
+        if (rc != PBX_OK) { pbx_plan_destroy(p); return rc; }
+    }
     e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { pbx_plan_destroy(p); return cuda_fail(e, "cudaStreamCreate"); }
     *out = p;
@@ -392,6 +439,8 @@ int pbx_plan_destroy(pbx_plan* p) {
     DeviceGuard guard(p->device);
     cudaDeviceSynchronize();
     if (p->dev_tables) cudaFree(p->dev_tables);
+    if (p->dev_int_tables) cudaFree(p->dev_int_tables);
+    if (p->dmma_tables) cudaFree(p->dmma_tables);
     if (p->scratch) cudaFree(p->scratch);
     if (p->io) cudaFree(p->io);
     if (p->stat_partials) cudaFree(p->stat_partials);

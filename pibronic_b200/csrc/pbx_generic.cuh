@@ -23,6 +23,12 @@ struct DevTables {
     const double *wcum;              // [Ar]
     const double *e_off, *l_off, *q_pack;  // [AA], [N][AA], [NN][AA]
     const double *samp;              // [P][N][3]
+    // coupling tables in FP64 tensor-core (mma.sync m8n8k4) fragment order, pbx_mid_bead_kernel:
+    // V[bead][k] = sum_f feature_f(bead) * coef[f][k], features = R_n R_m (n <= m), R_n, 1
+    const double *q_dmma;            // [KS][NT][32]: coef[4 ks + lane%4][8 j + lane/4]
+    const int *feat;                 // [4 KS]: rows (ra | rb << 16) of the coordinate tile whose product is feature f
+    const int *tri_ij;               // [8 NT]: (i << 16 | j) of packed entry k, -1 beyond AA
+    int KS, NT;
 };
 
 struct BeadOutputs {

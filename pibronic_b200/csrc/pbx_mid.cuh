@@ -5,9 +5,10 @@
 //   pbx_mid_sample_kernel : thread per (sample, MODE PAIR) -- the N ring recurrences are independent,
 //                           so a 2400-sample chunk yields N/2 times more threads than thread-per-sample
 //   pbx_mid_bead_kernel   : one warp per MID_IB = 8 consecutive beads of a sample.  The coupling matrix
-//                           V[item][k] = e_off[k] + sum_n R_n (l_off[n][k] + sum_{m>=n} q[n,m][k] R_m) is
-//                           accumulated for the 8 beads at once: every element of the packed Q table
-//                           (187 KB at c4) fetched from L1/L2 feeds 8 FMAs; lanes own packed entries k.
+//                           V[bead][k] = e_off[k] + sum_n R_n l_off[n][k] + sum_{n<=m} q[n,m][k] R_n R_m is a
+//                           dense (8 beads x 325 features) x (325 x 78) contraction at c4: it runs on the FP64
+//                           tensor cores (mma.sync.m8n8k4.f64), 10 MMAs per 4 features, the table pre-tiled in
+//                           fragment order (210 KB, read as coalesced 256-byte rows from L1/L2).
 //                           exp(-tau V) uses a register-blocked 4x8-lane product (5 shared loads per
 //                           6 FMAs at A=12 instead of 2 per FMA).
 //   pbx_mid_chain_kernel  : lane = (sample, row i): the rows of the three chained products live in
@@ -74,7 +75,7 @@ pbx_mid_sample_kernel(DevTables T, unsigned long long seed, long long first_samp
 // ---------------------------------------------------------------------------------------------
 template <int AT> struct MidShape {
     static constexpr int RI = (AT + 3) / 4, CJ = (AT + 7) / 8;
-    static constexpr int AA = AT * (AT + 1) / 2, KR = (AA + 31) / 32, AA2 = AT * AT;
+    static constexpr int AA = AT * (AT + 1) / 2, NT = (AA + 7) / 8, AA2 = AT * AT;   // NT: 8-wide mma tiles over the packed entries
 };
 
 template <int AT>
@@ -199,7 +200,7 @@ __device__ __forceinline__ const double* warp_expm_at(double* X, double* W0, dou
 
 // shared memory (doubles) of one warp of the bead kernel
 __host__ __device__ inline size_t mid_bead_warp_doubles(int A, int Ar, int N) {
-    size_t n = (size_t)N * MID_RS + (size_t)MID_IB * A * A + 4 * (size_t)A * A + (size_t)MID_IB * (3 * A + Ar);
+    size_t n = (size_t)(N + 1) * MID_RS + (size_t)MID_IB * A * A + 4 * (size_t)A * A + (size_t)MID_IB * (3 * A + Ar);
     return (n + 1) & ~(size_t)1;
 }
 
@@ -208,9 +209,9 @@ __host__ __device__ inline size_t mid_bead_warp_doubles(int A, int Ar, int N) {
 // ---------------------------------------------------------------------------------------------
 template <int AT>
 __global__ void __launch_bounds__(MID_WARPS * 32)
-pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_samples, BeadOutputs out, int has_q) {
+pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_samples, BeadOutputs out) {
     extern __shared__ __align__(16) double sm[];
-    constexpr int KR = MidShape<AT>::KR, AA = MidShape<AT>::AA, AA2 = AT * AT;
+    constexpr int AA2 = AT * AT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Ar = T.Ar, N = T.N, P = T.P;
     const int groups = (P + MID_IB - 1) / MID_IB;
@@ -220,8 +221,8 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
     const int p0 = (int)(gid - x * groups) * MID_IB;
     const int nb = min(MID_IB, P - p0);
     double* w = sm + (size_t)warp * mid_bead_warp_doubles(AT, Ar, N);
-    double* Rt = w;                               // [N][MID_RS]: beads p0 .. p0+MID_IB (ring closed)
-    double* Xs = Rt + (size_t)N * MID_RS;         // [MID_IB][AT][AT]
+    double* Rt = w;                               // [N + 1][MID_RS]: beads p0 .. p0+MID_IB (ring closed); row N = ones
+    double* Xs = Rt + (size_t)(N + 1) * MID_RS;   // [MID_IB][AT][AT]
     double* W0 = Xs + (size_t)MID_IB * AA2;       // 4 work matrices
     double *W1 = W0 + AA2, *W2 = W1 + AA2, *W3 = W2 + AA2;
     double* lall = W3 + AA2;                      // [MID_IB][3*AT + Ar] log factors
@@ -233,81 +234,52 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
         if (p >= P) p -= P;                        // bead P is bead 0; beyond that only padding
         Rt[n * MID_RS + jj] = (p0 + jj <= P) ? Rx[(size_t)n * P + p] : 0.0;
     }
+    if (lane < MID_RS) Rt[N * MID_RS + lane] = 1.0;
     __syncwarp();
     const size_t xp0 = (size_t)x * P + p0;
 
-    // ---- V for the beads of the group at once; lane owns packed entries k = lane + 32 r
+    // ---- V for the 8 beads of the group on the FP64 tensor cores: V[bead][k] = sum_f feat_f(bead) coef[f][k] is an
+    //      (8 x K) x (K x AA) product, K = N(N+1)/2 + N + 1 features (R_n R_m, R_n, 1).  One mma.sync.m8n8k4 per
+    //      (4 features, 8 packed entries): lane (r = lane/4, c = lane%4) forms its A element -- feature 4 ks + c of
+    //      bead r -- with one multiply, the B fragments are coalesced 256-byte rows of the pre-tiled table.
     if (out.v_mat || out.m_mat) {
-        int ki[KR], kj[KR];
-        bool kv[KR];
+        constexpr int NT = MidShape<AT>::NT;
+        double acc[NT][2];
 #pragma unroll
-        for (int r = 0; r < KR; ++r) {
-            const int k = lane + 32 * r;
-            kv[r] = k < AA;
-            int i = (int)((sqrt(8.0 * k + 1.0) - 1.0) * 0.5);
-            while (tri(i + 1, 0) <= k) ++i;
-            while (tri(i, 0) > k) --i;
-            ki[r] = i; kj[r] = k - tri(i, 0);
-        }
-        double acc[MID_IB][KR];
+        for (int j = 0; j < NT; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+        const int r = lane >> 2, c = lane & 3;
+        const double* qb = T.q_dmma + lane;
+        const double* Rr = Rt + r;
+#pragma unroll 2
+        for (int ks = 0; ks < T.KS; ++ks) {
+            const int f = __ldg(T.feat + 4 * ks + c);
+            const double a = Rr[(f & 0xffff) * MID_RS] * Rr[(f >> 16) * MID_RS];
 #pragma unroll
-        for (int r = 0; r < KR; ++r) {
-            const double e = kv[r] ? T.e_off[lane + 32 * r] : 0.0;
-#pragma unroll
-            for (int jj = 0; jj < MID_IB; ++jj) acc[jj][r] = e;
-        }
-        const double* qp = T.q_pack + lane;
-        for (int n = 0; n < N; ++n) {
-            double rn[MID_IB], inner[MID_IB][KR];
-#pragma unroll
-            for (int jj = 0; jj < MID_IB; jj += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(Rt + n * MID_RS + jj);
-                rn[jj] = v.x; rn[jj + 1] = v.y;
+            for (int j = 0; j < NT; ++j) {
+                const double b = __ldg(qb + ((size_t)ks * NT + j) * 32);
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc[j][0]), "+d"(acc[j][1]) : "d"(a), "d"(b));
             }
+        }
+        // accumulator layout: lane holds V[bead r][k = 8 j + 2 c + e], e = 0, 1
+        if (r < nb) {
 #pragma unroll
-            for (int r = 0; r < KR; ++r) {
-                const double lin = kv[r] ? T.l_off[(size_t)n * AA + lane + 32 * r] : 0.0;
+            for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int jj = 0; jj < MID_IB; ++jj) inner[jj][r] = lin;
-            }
-            if (has_q) {
-                for (int m = n; m < N; ++m) {
-                    double q[KR], rm[MID_IB];
-#pragma unroll
-                    for (int r = 0; r < KR; ++r) q[r] = kv[r] ? __ldg(qp + 32 * r) : 0.0;
-#pragma unroll
-                    for (int jj = 0; jj < MID_IB; jj += 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(Rt + m * MID_RS + jj);
-                        rm[jj] = v.x; rm[jj + 1] = v.y;
+                for (int e = 0; e < 2; ++e) {
+                    const int ij = __ldg(T.tri_ij + 8 * j + 2 * c + e);
+                    if (ij < 0) continue;
+                    const int i = ij >> 16, jj2 = ij & 0xffff;
+                    const double v = acc[j][e];
+                    if (out.v_mat) {
+                        out.v_mat[(xp0 + r) * AA2 + i * AT + jj2] = v;
+                        out.v_mat[(xp0 + r) * AA2 + jj2 * AT + i] = v;
                     }
-#pragma unroll
-                    for (int r = 0; r < KR; ++r)
-#pragma unroll
-                        for (int jj = 0; jj < MID_IB; ++jj) inner[jj][r] = fma(q[r], rm[jj], inner[jj][r]);
-                    qp += AA;
+                    Xs[(size_t)r * AA2 + i * AT + jj2] = v * T.neg_tau;
+                    Xs[(size_t)r * AA2 + jj2 * AT + i] = v * T.neg_tau;
                 }
-            }
-#pragma unroll
-            for (int r = 0; r < KR; ++r)
-#pragma unroll
-                for (int jj = 0; jj < MID_IB; ++jj) acc[jj][r] = fma(rn[jj], inner[jj][r], acc[jj][r]);
         }
-#pragma unroll
-        for (int r = 0; r < KR; ++r) {
-            if (!kv[r]) continue;
-            const int i = ki[r], j = kj[r];
-#pragma unroll
-            for (int jj = 0; jj < MID_IB; ++jj) {
-                if (jj >= nb) break;
-                const double v = acc[jj][r];
-                if (out.v_mat) {
-                    out.v_mat[(xp0 + jj) * AA2 + i * AT + j] = v;
-                    out.v_mat[(xp0 + jj) * AA2 + j * AT + i] = v;
-                }
-                Xs[(size_t)jj * AA2 + i * AT + j] = v * T.neg_tau;
-                Xs[(size_t)jj * AA2 + j * AT + i] = v * T.neg_tau;
-            }
-        }
+        __syncwarp();
     }
 
     // ---- O factors in log space for the beads of the group at once; work items (set, surface)
