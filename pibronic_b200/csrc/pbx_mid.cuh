@@ -130,7 +130,7 @@ __device__ __forceinline__ void blk_load(const double* __restrict__ src, LaneBlo
             C.v[ri][cj] = src[min(li + 4 * ri, AT - 1) * AT + min(lj + 8 * cj, AT - 1)];
 }
 
-// M = exp(X) (degree-12 Taylor, Paterson-Stockmeyer, scaling and squaring as in sym_expm); X in shared
+// M = exp(X) (degree-12 Taylor in four products, scaling and squaring as in sym_expm); X in shared
 // memory is overwritten by its scaled copy; W0..W3 are AT*AT work matrices; the result is left in the
 // lane blocks `out` AND in shared memory at the returned pointer.
 template <int AT>
@@ -149,42 +149,42 @@ __device__ __forceinline__ const double* warp_expm_at(double* X, double* W0, dou
     const double scale = __hiloint2double((1023 - s) << 20, 0);
     for (int e = lane; e < AA2; e += 32) X[e] *= scale;
     __syncwarp();
-    LaneBlock<AT> x1, x2, x3, x4, b;
+    // four-product degree-12 Taylor polynomial (pbx_device.cuh, namespace t12)
+    LaneBlock<AT> x1, x2, x3, y0, b;
+    auto diag = [&](int ri, int cj) { return (li + 4 * ri) == (lj + 8 * cj); };
     blk_load<AT>(X, x1, li, lj);
     blk_matmul<AT>(X, X, x2, li, lj);
     blk_store<AT>(W0, x2, li, lj);          // W0 = X^2
     __syncwarp();
-    blk_matmul<AT>(X, W0, x3, li, lj);      // X^3 (registers only)
-    blk_matmul<AT>(W0, W0, x4, li, lj);
-    blk_store<AT>(W1, x4, li, lj);          // W1 = X^4
-    constexpr double c2 = 1.0 / 2, c3 = 1.0 / 6, c4 = 1.0 / 24, c5 = 1.0 / 120, c6 = 1.0 / 720, c7 = 1.0 / 5040,
-                     c8 = 1.0 / 40320, c9 = 1.0 / 362880, c10 = 1.0 / 3628800, c11 = 1.0 / 39916800,
-                     c12 = 1.0 / 479001600;
-    auto diag = [&](int ri, int cj) { return (li + 4 * ri) == (lj + 8 * cj); };
+    blk_matmul<AT>(X, W0, x3, li, lj);
+    blk_store<AT>(W1, x3, li, lj);          // W1 = X^3
 #pragma unroll
     for (int ri = 0; ri < RI; ++ri)
 #pragma unroll
         for (int cj = 0; cj < CJ; ++cj)
-            b.v[ri][cj] = fma(c12, x4.v[ri][cj], fma(c11, x3.v[ri][cj], fma(c10, x2.v[ri][cj], c9 * x1.v[ri][cj]))) +
-                          (diag(ri, cj) ? c8 : 0.0);
+            b.v[ri][cj] = fma(t12::c1, x3.v[ri][cj], fma(t12::c2, x2.v[ri][cj], t12::c3 * x1.v[ri][cj]));
     blk_store<AT>(W2, b, li, lj);
     __syncwarp();
-    blk_matmul<AT>(W1, W2, out, li, lj);    // X^4 * B2
+    blk_matmul<AT>(W1, W2, y0, li, lj);     // Y0 = X^3 (c1 X^3 + c2 X^2 + c3 X)
+    __syncwarp();                           // W2 is rewritten below
 #pragma unroll
     for (int ri = 0; ri < RI; ++ri)
 #pragma unroll
-        for (int cj = 0; cj < CJ; ++cj)
-            b.v[ri][cj] = out.v[ri][cj] + fma(c7, x3.v[ri][cj], fma(c6, x2.v[ri][cj], c5 * x1.v[ri][cj])) +
-                          (diag(ri, cj) ? c4 : 0.0);
-    blk_store<AT>(W3, b, li, lj);
+        for (int cj = 0; cj < CJ; ++cj) {
+            b.v[ri][cj] = y0.v[ri][cj] + fma(t12::c4, x3.v[ri][cj], fma(t12::c5, x2.v[ri][cj], t12::c6 * x1.v[ri][cj]));
+            out.v[ri][cj] = y0.v[ri][cj] + fma(t12::c7, x3.v[ri][cj], t12::c8 * x2.v[ri][cj]);
+        }
+    blk_store<AT>(W2, b, li, lj);
+    blk_store<AT>(W3, out, li, lj);
     __syncwarp();
-    blk_matmul<AT>(W1, W3, out, li, lj);
+    blk_matmul<AT>(W2, W3, out, li, lj);
 #pragma unroll
     for (int ri = 0; ri < RI; ++ri)
 #pragma unroll
         for (int cj = 0; cj < CJ; ++cj)
-            out.v[ri][cj] = out.v[ri][cj] + fma(c3, x3.v[ri][cj], fma(c2, x2.v[ri][cj], x1.v[ri][cj])) +
+            out.v[ri][cj] = out.v[ri][cj] + fma(t12::c9, y0.v[ri][cj], fma(t12::c10, x3.v[ri][cj], fma(0.5, x2.v[ri][cj], x1.v[ri][cj]))) +
                             (diag(ri, cj) ? 1.0 : 0.0);
+    __syncwarp();                           // all lanes are done reading W2, W3
     double* cur = W2;
     double* nxt = W3;
     blk_store<AT>(cur, out, li, lj);
