@@ -18,6 +18,7 @@
 // Reference path reproduced per sample: /root/reference/pibronic/pimc/pimc.py:1420-1449
 // (block_compute_pm body) with the helpers at 1062-1213; SURVEY.md App. A.
 #pragma once
+#include <algorithm>
 #include <type_traits>
 
 #include "pbx_device.cuh"
@@ -252,9 +253,6 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
     constexpr int TB = PBX_TILE;
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nt = blockDim.x;
-    long long x = (long long)blockIdx.x * nt + tid;
-    const bool live = x < L.n_samples;
-    if (!live) x = L.n_samples - 1;       // keep the thread in step with its CTA; its result is dropped
     const int P = T.P;
     // per-thread columns: element i of this thread lives at base[i * nt]
     double* tile = smem + tid;                               // [(TB+1)][N]
@@ -262,9 +260,8 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
     double* yprev = y0 + (size_t)N * nt;                     // [N]
     double* dsrc = yprev + (size_t)N * nt;                   // [N] shift of the mixture component drawn
 
-    if (MODE == MODE_REDO) {
-        if (!live || !isnan(L.out4[x])) return;   // no block-wide barrier in this kernel: threads may leave
-    }
+    // everything that depends on the sample index; MODE_REDO calls it for every flagged sample of a grid-stride scan
+    auto process = [&](const long long x, const bool live) {
     const unsigned long long gidx = (unsigned long long)(L.first_sample + x);
     const uint2 key = make_uint2((uint32_t)L.seed, (uint32_t)(L.seed >> 32));
     if (MODE != MODE_COORDS) {
@@ -395,6 +392,17 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
 #pragma unroll
         for (int v = 0; v < NV; ++v) L.mirror[(size_t)(1 + v) * L.mirror_ld + x] = tr[v];
     }
+    };   // process
+
+    if constexpr (MODE == MODE_REDO) {
+        // no block-wide barrier in this kernel: every thread scans its own stride of the result array
+        for (long long x = (long long)blockIdx.x * nt + tid; x < L.n_samples; x += (long long)gridDim.x * nt)
+            if (isnan(L.out4[x])) process(x, true);
+    } else {
+        const long long x = (long long)blockIdx.x * nt + tid;
+        const bool live = x < L.n_samples;
+        process(live ? x : L.n_samples - 1, live);   // a dead thread stays in step with its CTA; its result is dropped
+    }
 }
 
 // type-erased launcher stored in the plan
@@ -431,7 +439,8 @@ void fill_fast_tables(const HostTables& H, void* dst) {
 template <int A, int N, int AR, int MODE, bool PM, bool JACOBI, bool SHARE>
 cudaError_t launch_one(const FastTables<A, N, AR>& T, const FastLaunch& L, cudaStream_t stream) {
     const int threads = PBX_BLOCK;
-    const long long blocks = (L.n_samples + threads - 1) / threads;
+    long long blocks = (L.n_samples + threads - 1) / threads;
+    if (MODE == MODE_REDO) blocks = std::min<long long>(blocks, 2 * 148);   // grid-stride scan
     const size_t smem = (size_t)fast_smem_doubles_per_thread<N>() * threads * sizeof(double);
     auto kernel = pbx_fast_kernel<A, N, AR, MODE, PM, JACOBI, SHARE>;
     if (smem > 48 * 1024) {

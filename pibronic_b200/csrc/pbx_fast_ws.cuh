@@ -260,10 +260,13 @@ cudaError_t launch_ws_one(const FastTables<A, N, AR>& T, const FastLaunch& L, cu
 }
 
 // number of kernels one warp-specialised launch enqueues
-inline int ws_launches(bool pm) { return (pm && PBX_DELTA_EXP) ? 2 : 1; }
+template <int N>
+int ws_launches(bool pm) { return (ws_smem_bytes<N>() <= 227 * 1024 && pm && PBX_DELTA_EXP) ? 2 : 1; }
 
 template <int A, int N, int AR>
 cudaError_t launch_fast_ws(const void* tables, const FastLaunch& L, bool pm, bool share, cudaStream_t stream) {
+    if constexpr (ws_smem_bytes<N>() > 227 * 1024)      // ring does not fit an SM: one-role kernel
+        return launch_fast<A, N, AR>(tables, L, MODE_SAMPLE, pm, false, share, stream);
     const auto& T = *reinterpret_cast<const FastTables<A, N, AR>*>(tables);
     if constexpr (A == AR) {
         if (share) return pm ? launch_ws_one<A, N, AR, true, true>(T, L, stream) : launch_ws_one<A, N, AR, false, true>(T, L, stream);
@@ -274,7 +277,7 @@ cudaError_t launch_fast_ws(const void* tables, const FastLaunch& L, bool pm, boo
 template <int A, int N, int AR>
 constexpr FastKernelEntry make_entry() {
     return FastKernelEntry{A, N, AR, sizeof(FastTables<A, N, AR>), &fill_fast_tables<A, N, AR>, &launch_fast<A, N, AR>,
-                           &launch_fast_ws<A, N, AR>, &ws_launches};
+                           &launch_fast_ws<A, N, AR>, &ws_launches<N>};
 }
 
 }  // namespace pbx
