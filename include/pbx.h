@@ -59,8 +59,9 @@ enum {
     PBX_FLAG_PM             = 1u << 0, /* also evaluate g(beta +/- delta_beta): block_compute_pm          */
     PBX_QUIRK_RHO_TRUNC     = 1u << 1, /* reference quirk pimc.py:1110-1111: rho(R) uses only the first   */
                                        /* min(A, A_rho) sampling surfaces (bit-parity runs with A_rho > A) */
-    PBX_FLAG_M_TAU_PM       = 1u << 2, /* use tau+/- (not tau) in M for g+/- (reference uses tau,         */
-                                       /* pimc.py:1183); off = bug-compatible default. Reserved.          */
+    PBX_FLAG_M_TAU_PM       = 1u << 2, /* g+/- use exp(-tau+/- V), the consistent beta +/- delta_beta      */
+                                       /* estimator; off = the reference's exp(-tau V) for all three       */
+                                       /* (pimc.py:1183).  Needs PBX_FLAG_PM and a register-resident shape. */
     PBX_FLAG_EIG_JACOBI     = 1u << 3, /* M = U exp(-tau lambda) U^T by a Jacobi eigensolve (reference's  */
                                        /* formulation); default is a scaling-and-squaring exp(-tau V)      */
     PBX_FLAG_FORCE_GENERIC  = 1u << 4, /* never use the register-resident small-A kernels                 */

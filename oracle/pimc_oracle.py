@@ -271,10 +271,11 @@ def coupling_matrices(tab, R):
     return V
 
 
-def m_matrices(tab, V):
-    """M = U exp(-tau lambda) U^T -- always data.tau, also for the +/- variants (pimc.py:1171-1187, quirk Q2)."""
+def m_matrices(tab, V, tau=None):
+    """M = U exp(-tau lambda) U^T -- always data.tau, also for the +/- variants (pimc.py:1171-1187, quirk Q2).
+    `tau` overrides it for the consistent estimator (PBX_FLAG_M_TAU_PM), which the reference does not have."""
     lam, U = np.linalg.eigh(V, UPLO="L")
-    return np.einsum("abcd,abd,abed->abce", U, np.exp(-tab.tau * lam), U, optimize="optimal")
+    return np.einsum("abcd,abd,abed->abce", U, np.exp(-(tab.tau if tau is None else tau) * lam), U, optimize="optimal")
 
 
 def chain_trace(M, o_diag, faithful=True):
@@ -303,9 +304,10 @@ def chain_trace(M, o_diag, faithful=True):
     return np.trace(acc, axis1=1, axis2=2)
 
 
-def estimate_block(tab, R, pm=True, faithful=True, scale=True, details=None):
+def estimate_block(tab, R, pm=True, faithful=True, scale=True, details=None, m_tau_pm=False):
     """(rho, g[, g_plus, g_minus]) for bead coordinates R (B,N,P); order of operations of
-    block_compute / block_compute_pm (pimc.py:1364-1381, 1420-1449)."""
+    block_compute / block_compute_pm (pimc.py:1364-1381, 1420-1449).
+    m_tau_pm=True is NOT the reference: g+- then use exp(-tau+- V) (PBX_FLAG_M_TAU_PM)."""
     n_rho = min(tab.A, tab.Ar) if tab.rho_trunc else None
     o_rho = o_factors(R, tab.d_rho, tab.rho, n_rho)
     o_vib = o_factors(R, tab.d_vib, tab.vib)
@@ -324,9 +326,9 @@ def estimate_block(tab, R, pm=True, faithful=True, scale=True, details=None):
     if not pm:
         return rho, g
     o_p = o_factors(R, tab.d_vib, tab.vib_plus) / S[..., None]
-    gp = chain_trace(M, o_p, faithful)
+    gp = chain_trace(m_matrices(tab, V, tab.vib_plus.tau) if m_tau_pm else M, o_p, faithful)
     o_m = o_factors(R, tab.d_vib, tab.vib_minus) / S[..., None]
-    gm = chain_trace(M, o_m, faithful)
+    gm = chain_trace(m_matrices(tab, V, tab.vib_minus.tau) if m_tau_pm else M, o_m, faithful)
     return rho, g, gp, gm
 
 

@@ -210,7 +210,7 @@ struct pbx_plan {
     HostTables H;
     int device = 0;
     uint32_t flags = 0;
-    bool pm = false, jacobi = false, scale = true;
+    bool pm = false, jacobi = false, scale = true, mtau = false;
     double* dev_tables = nullptr;
     int* dev_int_tables = nullptr;
     double* dmma_tables = nullptr;
@@ -421,6 +421,12 @@ int pbx_plan_create(const pbx_model* vib, const pbx_rho* rho, int32_t beads, dou
     p->pm = flags & PBX_FLAG_PM; p->jacobi = flags & PBX_FLAG_EIG_JACOBI; p->scale = !(flags & PBX_FLAG_NO_SCALING);
     const bool want_fast = !(flags & PBX_FLAG_FORCE_GENERIC) && p->scale;
     if (want_fast) p->fast = find_fast_kernel(p->H.A, p->H.N, p->H.Ar);
+    p->mtau = flags & PBX_FLAG_M_TAU_PM;
+    if (p->mtau && (!p->pm || p->jacobi || !p->fast)) {
+        delete p;
+        return fail(PBX_ERR_UNSUPPORTED, "PBX_FLAG_M_TAU_PM needs PBX_FLAG_PM, the default exp(-tau V) builder and a model shape "
+                                         "with a register-resident kernel (csrc/shapes.def)");
+    }
     if (p->fast) {
         p->fast_tables.assign(p->fast->table_bytes, 0);
         p->fast->fill(p->H, p->fast_tables.data());
@@ -512,11 +518,11 @@ int sample_eval_impl(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n
         L.samp = p->D.samp; L.seed = seed; L.first_sample = first_sample; L.n_samples = n; L.out4 = out4; L.out_ld = n;
         L.mirror = mirror; L.mirror_ld = mirror_ld;
         if (!p->jacobi && !(p->flags & PBX_FLAG_NO_WARPSPEC)) {   // producer/consumer warps (pbx_fast_ws.cuh)
-            PBX_CUDA(p->fast->launch_ws(p->fast_tables.data(), L, p->pm, p->H.rho_shares_vib, st));
-            p->launches += p->fast->ws_kernels(p->pm);
+            PBX_CUDA(p->fast->launch_ws(p->fast_tables.data(), L, p->pm, p->H.rho_shares_vib, p->mtau, st));
+            p->launches += p->fast->ws_kernels(p->pm, p->mtau);
             return PBX_OK;
         }
-        PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_SAMPLE, p->pm, p->jacobi, p->H.rho_shares_vib, st));
+        PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_SAMPLE, p->pm, p->jacobi, p->H.rho_shares_vib, p->mtau, st));
         p->launches += 1;
         return PBX_OK;
     }
@@ -578,7 +584,7 @@ int pbx_eval_coords_dev(pbx_plan* p, const double* R, int64_t n, double* out4, v
             FastLaunch L{};
             L.samp = p->D.samp; L.coords_t = (const double*)p->scratch; L.ld = ld; L.n_samples = m;
             L.out4 = out4 + off; L.out_ld = n;
-            PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_COORDS, p->pm, p->jacobi, p->H.rho_shares_vib, st));
+            PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_COORDS, p->pm, p->jacobi, p->H.rho_shares_vib, p->mtau, st));
             p->launches += 2;
         }
         return PBX_OK;

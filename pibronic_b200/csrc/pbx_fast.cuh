@@ -61,6 +61,7 @@ struct FastTables {
     double e_off[AA];     // the three coupling tables are pre-multiplied by -tau: the kernel builds X = -tau V directly
     double l_off[N][AA];  // (M always uses tau, also for g+-: reference quirk Q2, pimc.py:1183)
     double q_pack[NN][AA];
+    double kappa;         // delta_beta / beta = tau+/tau - 1 (PBX_FLAG_M_TAU_PM)
     int P;
     int n_rho_eval;
 };
@@ -99,7 +100,10 @@ __device__ __forceinline__ bool exp_small_out_of_range(double d) {
 // one bead of the estimator: updates the chained products Tm and the log-accumulators of rho
 // SAFE = false: O(tau+-) = O(tau) * exp_small(delta) unconditionally, `bad` records |delta| >= 2^-8 (the caller then
 // redoes the sample with SAFE = true, full exponentials) -- keeps the hot loop free of a data dependent branch
-template <int A, int N, int AR, bool PM, bool JACOBI, bool SHARE, bool SAFE>
+// MTAU (PBX_FLAG_M_TAU_PM): g+- use M(tau+-) = exp(-tau+- V) = M exp(+-kappa X), X = -tau V, instead of the reference's
+// M(tau) for all three (quirk Q2); the correction exp(+-Y) - I = +-Y + Y^2/2, Y = kappa X, is exact to rounding for
+// ||Y|| < 2^-14 (next term ||Y||^3/6 < 4e-14 at the bound, 1e-19 at the reference's delta_beta), else `bad`
+template <int A, int N, int AR, bool PM, bool JACOBI, bool SHARE, bool SAFE, bool MTAU = false>
 __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const double (&Rc)[N], const double (&Rn)[N],
                                           double (&Tm)[PM ? 3 : 1][A][A], double (&lrho)[AR], bool& bad) {
     constexpr int AA = A * (A + 1) / 2;
@@ -221,21 +225,53 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
 #pragma unroll
             for (int k = 0; k < AA; ++k) X[k] = fma(T.q_pack[pair_index(n, m, N)][k], rr, X[k]);
         }
-    double M[AA];
-    if (JACOBI) sym_exp_jacobi<A>(X, M);
-    else sym_expm<A>(X, M);
+    double M[AA], Mpm[(PM && MTAU) ? 2 : 1][AA];
+    if (PM && MTAU) {
+        if (SAFE) {                 // full exponentials of -tau+- V
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                double Xw[AA];
+                const double f = (w == 0) ? 1.0 + T.kappa : 1.0 - T.kappa;
+#pragma unroll
+                for (int k = 0; k < AA; ++k) Xw[k] = f * X[k];
+                if (JACOBI) sym_exp_jacobi<A>(Xw, Mpm[w]);
+                else sym_expm<A>(Xw, Mpm[w]);
+            }
+            if (JACOBI) sym_exp_jacobi<A>(X, M);
+            else sym_expm<A>(X, M);
+        } else {
+            double Y[AA], Yh[AA], mass = 0.0;
+#pragma unroll
+            for (int k = 0; k < AA; ++k) { Y[k] = T.kappa * X[k]; mass += fabs(Y[k]); }
+            bad = bad || (__double2hiint(2.0 * mass) & 0x7fffffff) >= 0x3f100000;     // ||Y||_1 <= 2 mass >= 2^-14
+            if (JACOBI) sym_exp_jacobi<A>(X, M);
+            else sym_expm<A>(X, M);                       // scales X in place: Y was taken before
+            sym_mul<A>(Y, Y, Yh);
+            double Ep[AA], Em[AA];
+#pragma unroll
+            for (int k = 0; k < AA; ++k) { Ep[k] = fma(0.5, Yh[k], Y[k]); Em[k] = fma(0.5, Yh[k], -Y[k]); }
+            sym_mul<A>(M, Ep, Mpm[0]);
+            sym_mul<A>(M, Em, Mpm[1]);
+#pragma unroll
+            for (int k = 0; k < AA; ++k) { Mpm[0][k] += M[k]; Mpm[1][k] += M[k]; }
+        }
+    } else {
+        if (JACOBI) sym_exp_jacobi<A>(X, M);
+        else sym_expm<A>(X, M);
+    }
 
-    // ---- chain: T_v <- (T_v M) diag(O_v)
+    // ---- chain: T_v <- (T_v M_v) diag(O_v)
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
         for (int i = 0; i < A; ++i) {
+            const double (&Mv)[AA] = (PM && MTAU && v > 0) ? Mpm[v > 0 ? v - 1 : 0] : M;
             double row[A];
 #pragma unroll
             for (int j = 0; j < A; ++j) {
-                double acc = Tm[v][i][0] * M[sym(0, j)];
+                double acc = Tm[v][i][0] * Mv[sym(0, j)];
 #pragma unroll
-                for (int k = 1; k < A; ++k) acc = fma(Tm[v][i][k], M[sym(k, j)], acc);
+                for (int k = 1; k < A; ++k) acc = fma(Tm[v][i][k], Mv[sym(k, j)], acc);
                 row[j] = acc * O[v][j];
             }
 #pragma unroll
@@ -246,7 +282,7 @@ __device__ __forceinline__ void bead_step(const FastTables<A, N, AR>& T, const d
 // shared memory (doubles) per thread: (TILE+1) coordinate slots + sampler state y0, yprev, dsrc
 template <int N> constexpr int fast_smem_doubles_per_thread() { return (PBX_TILE + 1) * N + 3 * N; }
 
-template <int A, int N, int AR, int MODE, bool PM, bool JACOBI, bool SHARE>
+template <int A, int N, int AR, int MODE, bool PM, bool JACOBI, bool SHARE, bool MTAU = false>
 __global__ void __launch_bounds__(PBX_BLOCK, PBX_MIN_BLOCKS)
 pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch L) {
     constexpr int NV = PM ? 3 : 1;
@@ -356,7 +392,7 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
                     Rc[n] = tile[(size_t)(jj * N + n) * nt];
                     Rn[n] = tile[(size_t)((jj + 1) * N + n) * nt];
                 }
-                bead_step<A, N, AR, PM, JACOBI, SHARE, SAFE>(T, Rc, Rn, Tm, lrho, bad);
+                bead_step<A, N, AR, PM, JACOBI, SHARE, SAFE, MTAU>(T, Rc, Rn, Tm, lrho, bad);
             }
             // bead t0+TB becomes slot 0 of the next tile
 #pragma unroll
@@ -377,7 +413,7 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
         run_sample(std::true_type{});
     } else {
         bool redo = run_sample(std::false_type{});
-        if (PM && PBX_DELTA_EXP) {
+        if (PM && (PBX_DELTA_EXP || MTAU)) {
             if (__any_sync(__activemask(), redo)) {     // cold path: never taken at delta_beta/beta ~ 5e-6
                 if (redo) run_sample(std::true_type{});
             }
@@ -410,11 +446,11 @@ struct FastKernelEntry {
     int A, N, AR;
     size_t table_bytes;
     void (*fill)(const HostTables&, void* dst);
-    cudaError_t (*launch)(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share,
+    cudaError_t (*launch)(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share, bool mtau,
                           cudaStream_t stream);
     // warp-specialised sampler + estimator (pbx_fast_ws.cuh; scaling-and-squaring M only); enqueues `ws_kernels(pm)` kernels
-    cudaError_t (*launch_ws)(const void* tables, const FastLaunch& L, bool pm, bool share, cudaStream_t stream);
-    int (*ws_kernels)(bool pm);
+    cudaError_t (*launch_ws)(const void* tables, const FastLaunch& L, bool pm, bool share, bool mtau, cudaStream_t stream);
+    int (*ws_kernels)(bool pm, bool mtau);
 };
 
 template <int A, int N, int AR>
@@ -432,17 +468,18 @@ void fill_fast_tables(const HostTables& H, void* dst) {
     for (int k = 0; k < AA; ++k) T.e_off[k] = mt * H.e_off[k];
     for (int n = 0; n < N; ++n) for (int k = 0; k < AA; ++k) T.l_off[n][k] = mt * H.l_off[(size_t)n * AA + k];
     for (int q = 0; q < NN; ++q) for (int k = 0; k < AA; ++k) T.q_pack[q][k] = mt * H.q_pack[(size_t)q * AA + k];
+    T.kappa = H.delta_beta / H.beta;
     T.P = H.P;
     T.n_rho_eval = H.n_rho_eval;
 }
 
-template <int A, int N, int AR, int MODE, bool PM, bool JACOBI, bool SHARE>
+template <int A, int N, int AR, int MODE, bool PM, bool JACOBI, bool SHARE, bool MTAU = false>
 cudaError_t launch_one(const FastTables<A, N, AR>& T, const FastLaunch& L, cudaStream_t stream) {
     const int threads = PBX_BLOCK;
     long long blocks = (L.n_samples + threads - 1) / threads;
     if (MODE == MODE_REDO) blocks = std::min<long long>(blocks, 2 * 148);   // grid-stride scan
     const size_t smem = (size_t)fast_smem_doubles_per_thread<N>() * threads * sizeof(double);
-    auto kernel = pbx_fast_kernel<A, N, AR, MODE, PM, JACOBI, SHARE>;
+    auto kernel = pbx_fast_kernel<A, N, AR, MODE, PM, JACOBI, SHARE, MTAU>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -451,19 +488,21 @@ cudaError_t launch_one(const FastTables<A, N, AR>& T, const FastLaunch& L, cudaS
     return cudaGetLastError();
 }
 
-template <int A, int N, int AR, int MODE, bool PM, bool JACOBI>
+template <int A, int N, int AR, int MODE, bool PM, bool JACOBI, bool MTAU = false>
 cudaError_t launch_share(const FastTables<A, N, AR>& T, const FastLaunch& L, bool share, cudaStream_t stream) {
     if constexpr (A == AR) {
-        if (share) return launch_one<A, N, AR, MODE, PM, JACOBI, true>(T, L, stream);
+        if (share) return launch_one<A, N, AR, MODE, PM, JACOBI, true, MTAU>(T, L, stream);
     }
-    return launch_one<A, N, AR, MODE, PM, JACOBI, false>(T, L, stream);
+    return launch_one<A, N, AR, MODE, PM, JACOBI, false, MTAU>(T, L, stream);
 }
 
+// mtau (PBX_FLAG_M_TAU_PM) exists for the PM, scaling-and-squaring kernels only; pbx_plan_create rejects other combinations
 template <int A, int N, int AR>
-cudaError_t launch_fast(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share,
+cudaError_t launch_fast(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share, bool mtau,
                         cudaStream_t stream) {
     const auto& T = *reinterpret_cast<const FastTables<A, N, AR>*>(tables);
 #define PBX_DISPATCH(MODE_)                                                                               \
+    if (pm && mtau) return launch_share<A, N, AR, MODE_, true, false, true>(T, L, share, stream);        \
     if (pm) return jacobi ? launch_share<A, N, AR, MODE_, true, true>(T, L, share, stream)               \
                           : launch_share<A, N, AR, MODE_, true, false>(T, L, share, stream);             \
     return jacobi ? launch_share<A, N, AR, MODE_, false, true>(T, L, share, stream)                      \

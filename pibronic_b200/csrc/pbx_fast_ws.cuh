@@ -78,7 +78,7 @@ __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(ws_smem_u32(bar)), "r"(parity) : "memory");
 }
 
-template <int A, int N, int AR, bool PM, bool SHARE>
+template <int A, int N, int AR, bool PM, bool SHARE, bool MTAU = false>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch L) {
     constexpr int NV = PM ? 3 : 1;
@@ -212,7 +212,7 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
                 PBX_YP(n) = y;
                 Rn[n] = y + ds;
             }
-            bead_step<A, N, AR, PM, false, SHARE, false>(T, Rc, Rn, Tm, lrho, bad);
+            bead_step<A, N, AR, PM, false, SHARE, false, MTAU>(T, Rc, Rn, Tm, lrho, bad);
         }
         ws_mbar_arrive(empty_bar(g, s));
     }
@@ -224,7 +224,7 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
             Rc[n] = PBX_YP(n) + ds;
             Rn[n] = y0[n * WS_CONS] + ds;
         }
-        bead_step<A, N, AR, PM, false, SHARE, false>(T, Rc, Rn, Tm, lrho, bad);
+        bead_step<A, N, AR, PM, false, SHARE, false, MTAU>(T, Rc, Rn, Tm, lrho, bad);
     }
 #undef PBX_YP
     if (!live) return;
@@ -244,33 +244,37 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
     }
 }
 
-template <int A, int N, int AR, bool PM, bool SHARE>
+template <int A, int N, int AR, bool PM, bool SHARE, bool MTAU = false>
 cudaError_t launch_ws_one(const FastTables<A, N, AR>& T, const FastLaunch& L, cudaStream_t stream) {
     const long long blocks = (L.n_samples + WS_CONS - 1) / WS_CONS;
     constexpr size_t smem = ws_smem_bytes<N>();
-    auto kernel = pbx_fast_ws_kernel<A, N, AR, PM, SHARE>;
+    auto kernel = pbx_fast_ws_kernel<A, N, AR, PM, SHARE, MTAU>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kernel<<<(unsigned)blocks, WS_THREADS, smem, stream>>>(T, L);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (PM && PBX_DELTA_EXP)   // recompute the (normally zero) flagged samples with full exponentials
-        return launch_one<A, N, AR, MODE_REDO, PM, false, SHARE>(T, L, stream);
+    if (PM && (PBX_DELTA_EXP || MTAU))   // recompute the (normally zero) flagged samples with full exponentials
+        return launch_one<A, N, AR, MODE_REDO, PM, false, SHARE, MTAU>(T, L, stream);
     return cudaSuccess;
 }
 
 // number of kernels one warp-specialised launch enqueues
 template <int N>
-int ws_launches(bool pm) { return (ws_smem_bytes<N>() <= 227 * 1024 && pm && PBX_DELTA_EXP) ? 2 : 1; }
+int ws_launches(bool pm, bool mtau) { return (ws_smem_bytes<N>() <= 227 * 1024 && pm && (PBX_DELTA_EXP || mtau)) ? 2 : 1; }
 
 template <int A, int N, int AR>
-cudaError_t launch_fast_ws(const void* tables, const FastLaunch& L, bool pm, bool share, cudaStream_t stream) {
+cudaError_t launch_fast_ws(const void* tables, const FastLaunch& L, bool pm, bool share, bool mtau, cudaStream_t stream) {
     if constexpr (ws_smem_bytes<N>() > 227 * 1024)      // ring does not fit an SM: one-role kernel
-        return launch_fast<A, N, AR>(tables, L, MODE_SAMPLE, pm, false, share, stream);
+        return launch_fast<A, N, AR>(tables, L, MODE_SAMPLE, pm, false, share, mtau, stream);
     const auto& T = *reinterpret_cast<const FastTables<A, N, AR>*>(tables);
     if constexpr (A == AR) {
-        if (share) return pm ? launch_ws_one<A, N, AR, true, true>(T, L, stream) : launch_ws_one<A, N, AR, false, true>(T, L, stream);
+        if (share) {
+            if (pm && mtau) return launch_ws_one<A, N, AR, true, true, true>(T, L, stream);
+            return pm ? launch_ws_one<A, N, AR, true, true>(T, L, stream) : launch_ws_one<A, N, AR, false, true>(T, L, stream);
+        }
     }
+    if (pm && mtau) return launch_ws_one<A, N, AR, true, false, true>(T, L, stream);
     return pm ? launch_ws_one<A, N, AR, true, false>(T, L, stream) : launch_ws_one<A, N, AR, false, false>(T, L, stream);
 }
 

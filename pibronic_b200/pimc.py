@@ -292,6 +292,8 @@ class BoxData:
     quirk_rho_trunc = False  # reproduce pimc.py:1110-1111 when A_rho > A
     eig_jacobi = False       # M from a Jacobi eigensolve instead of the scaling-and-squaring exponential
     force_generic = False    # never use the register-resident kernels
+    m_tau_pm = False         # g+- with exp(-tau+- V) (consistent estimator, stats.consistent_jackknife_analysis); the
+                             # reference uses exp(-tau V) for all three (pimc.py:1183)
 
     _PM = False
 
@@ -470,6 +472,7 @@ class BoxData:
             flags |= _cabi.QUIRK_RHO_TRUNC if self.quirk_rho_trunc else 0
             flags |= _cabi.FLAG_EIG_JACOBI if self.eig_jacobi else 0
             flags |= _cabi.FLAG_FORCE_GENERIC if self.force_generic else 0
+            flags |= _cabi.FLAG_M_TAU_PM if (self.m_tau_pm and pm) else 0
             flags |= _cabi.FLAG_NO_SCALING if no_scaling else 0
             vib, rho = self.vib.raw, self.rho.raw
             self._plans[key] = _cabi.Plan(vib['energy'], vib['omega'], vib['linear'], vib['quadratic'],

@@ -15,7 +15,7 @@ from . import _cabi, constants, postprocessing as pp
 from .constants import boltzman
 from .pimc import BoxResultPM
 
-__all__ = ["add_harmonic_contribution", "basic_statistical_analysis", "basic_jackknife_analysis",
+__all__ = ["add_harmonic_contribution", "basic_statistical_analysis", "basic_jackknife_analysis", "consistent_jackknife_analysis",
            "starmap_wrapper", "statistical_analysis_of_pimc", "jackknife_analysis_of_pimc"]
 
 _BASIC_KEYS = ("Z", "Z error", "E", "E error", "Cv", "Cv error")
@@ -74,6 +74,24 @@ def basic_jackknife_analysis(temperature, pimc_result, analytic_data):
     for key, value in jk_dict.items():
         output_dict["jk_" + key] = value
     return output_dict
+
+
+def consistent_jackknife_analysis(temperature, pimc_result, analytic_data=None):
+    """NOT in the reference.  For results computed with ``data.m_tau_pm = True`` (PBX_FLAG_M_TAU_PM: g+- built with
+    exp(-tau+- V)) the finite differences of g already carry the whole beta dependence of Z = Z_rho <g/rho>:
+
+        E = -<d1>/<r>,   Cv = (<d2>/<r> - E^2) / (kB T^2)          -- nothing is added.
+
+    The reference's "basic" estimator differentiates only the harmonic factors (M always uses tau, pimc.py:1183) and then
+    adds E and Cv of the sampling model (stats.py:126-130); on the reference's own test model data_set_1 that gives
+    E = +0.104, Cv = 3.7e-3 against the sum-over-states values -0.4233 and 1.53e-4, which this estimator reproduces
+    within its jackknife error (tests/test_gpu_parity.py::test_pimc_reproduces_the_sum_over_states_thermodynamics).
+    If `analytic_data` has "Z" (the sampling model's partition function) Z is returned in absolute units."""
+    out = _device_statistics(temperature, pimc_result)
+    if analytic_data is not None and "Z" in analytic_data:
+        out["Z"] *= analytic_data["Z"]
+        out["Z error"] *= analytic_data["Z"]
+    return out
 
 
 def starmap_wrapper(FS, P, T, statistical_operation):

@@ -615,3 +615,92 @@ def test_large_delta_beta_takes_the_safe_path(cuda, delta_beta):
         R, _ = drawn_coords(cuda, plan, 3, 0, n)
         assert rel_err(fused, oracle_eval(tab, R)) < RTOL, name
         plan.close()
+
+
+# ------------------------------------------------------------------ the consistent estimator (PBX_FLAG_M_TAU_PM)
+def test_consistent_estimator_matches_oracle(cuda, case):
+    """g+- with exp(-tau+- V) -- not the reference's estimator (it keeps exp(-tau V), pimc.py:1183) -- against the oracle
+    with the same option, on the reference's coordinates and through the fused call; rho and g do not change"""
+    from oracle import pimc_oracle as orc
+    base = _cabi.FLAG_PM | _cabi.QUIRK_RHO_TRUNC
+    ref_plan = case.plan(base)
+    if not ref_plan.is_fast:
+        ref_plan.close()
+        with pytest.raises(_cabi.PbxError):
+            case.plan(base | _cabi.FLAG_M_TAU_PM)
+        return
+    plan = case.plan(base | _cabi.FLAG_M_TAU_PM)
+    tab = case.oracle_tables(rho_trunc=True)
+    want = np.stack(orc.estimate_block(tab, case.R, pm=True, faithful=False, m_tau_pm=True))
+    got = plan.eval_coords_host(case.R)
+    assert rel_err(got, want) < RTOL
+    quirk = ref_plan.eval_coords_host(case.R)
+    coupled = max(np.abs(tab.E_off).max(), np.abs(tab.L_off).max(), np.abs(tab.Q).max()) > 0    # else V = 0 and M = 1
+    assert np.array_equal(got[:2], quirk[:2]) and np.array_equal(got[2:], quirk[2:]) != coupled
+    n = 300
+    fused = plan.sample_eval_host(17, 3, n)
+    Rd, _ = drawn_coords(cuda, plan, 17, 3, n)
+    assert rel_err(fused, np.stack(orc.estimate_block(tab, Rd, pm=True, faithful=False, m_tau_pm=True))) < RTOL
+    one_role = case.plan(base | _cabi.FLAG_M_TAU_PM | _cabi.FLAG_NO_WARPSPEC)
+    assert np.array_equal(fused, one_role.sample_eval_host(17, 3, n))
+    for p in (plan, ref_plan, one_role):
+        p.close()
+
+
+def test_consistent_estimator_with_a_large_delta_beta(cuda):
+    """delta_beta so large that exp(+-kappa X) is no small correction: the flagged samples take the full-exponential path"""
+    from conftest import GoldenCase
+    from oracle import pimc_oracle as orc
+    case = GoldenCase("c2_4x6")
+    for delta_beta in (0.5, 5.0):
+        plan = _cabi.Plan(case.vib["E"], case.vib["w"], case.vib["L"], case.vib["Q"], case.rho["E"], case.rho["w"],
+                          case.rho["L"], case.P, orc.beta_of(case.T), delta_beta, flags=_cabi.FLAG_PM | _cabi.FLAG_M_TAU_PM, device=0)
+        tab = orc.precompute(case.vib, case.rho, case.P, case.T, delta_beta=delta_beta)
+        n = 200
+        fused = plan.sample_eval_host(3, 0, n)
+        Rd, _ = drawn_coords(cuda, plan, 3, 0, n)
+        assert rel_err(fused, np.stack(orc.estimate_block(tab, Rd, pm=True, faithful=False, m_tau_pm=True))) < RTOL
+        assert rel_err(plan.eval_coords_host(case.R),
+                       np.stack(orc.estimate_block(tab, case.R, pm=True, faithful=False, m_tau_pm=True))) < RTOL
+        plan.close()
+
+
+def test_pimc_reproduces_the_sum_over_states_thermodynamics(cuda):
+    """End to end against EXACT numbers: the reference's test model data_set_1 sampled from its rho_1, 2e7 samples of 64
+    beads (40 ms), vs the sum-over-states Z, E, Cv its Julia dependency computed (tests/golden/sos/).
+    Z = Z_rho <g/rho> is the reference's estimator.  E and Cv agree only with the consistent estimator (PBX_FLAG_M_TAU_PM,
+    nothing added); the reference's (exp(-tau V) for g+-, sampling-model E and Cv added) misses both by a wide margin."""
+    import json
+    from os.path import join
+    from conftest import GOLDEN
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import analytic, constants
+    sos_dir = join(GOLDEN, "sos")
+    vib = orc.load_vibronic_json(join(sos_dir, "coupled_model.json"))
+    rho = orc.load_sampling_json(join(sos_dir, "sampling_model.json"))
+    with open(join(sos_dir, "sos_B80.json")) as fh:
+        sos = {k: v[0] for k, v in json.load(fh).items()}
+    T, P, X = 300.0, 64, 20_000_000
+    # the closed-form sampling-model numbers (analytic.py) are the Julia ones
+    tilde = rho["E"] - 0.5 * (rho["L"] ** 2 / rho["w"][:, None]).sum(axis=0)
+    mine = analytic.thermodynamics(tilde, rho["w"], constants.beta(T))
+    # (to 1e-6: the Julia side used beta = 38.68174037, pibronic/constants.py gives 38.68174020)
+    assert np.isclose(mine["Z_sampling"], sos["Z_sampling"], rtol=1e-6) and np.isclose(mine["E_sampling"], sos["E_sampling"], rtol=1e-6)
+    out = cuda.empty((4, X), dtype=cuda.float64, device="cuda")
+    results = {}
+    for name, flags in (("consistent", _cabi.FLAG_PM | _cabi.FLAG_M_TAU_PM), ("reference", _cabi.FLAG_PM)):
+        plan = _cabi.Plan(vib["E"], vib["w"], vib["L"], vib["Q"], rho["E"], rho["w"], rho["L"], P, constants.beta(T),
+                          constants.delta_beta, flags=flags, device=0)
+        plan.sample_eval(2090, 0, X, out)
+        results[name] = plan.stats(out, X)
+        plan.close()
+    st = results["consistent"]
+    Z, dZ = st["Z"] * mine["Z_sampling"], st["Z error"] * mine["Z_sampling"]
+    # Trotter error at P = 64 is +0.65 % in Z, -4.5e-4 in E (tools/sos_check.py shows the convergence with P)
+    assert abs(Z - sos["Z_coupled"] * 1.0065) < 5 * dZ + 2e-3 * sos["Z_coupled"]
+    assert np.array_equal(results["reference"]["Z"], st["Z"])                         # rho and g do not depend on the flag
+    assert abs(st["jk_E"] - sos["E_coupled"]) < 5 * st["jk_E error"] + 1e-3
+    assert abs(st["jk_Cv"] - sos["Cv_coupled"]) < 5 * st["jk_Cv error"] + 0.05 * sos["Cv_coupled"]
+    ref = results["reference"]
+    assert abs(ref["jk_E"] + sos["E_sampling"] - sos["E_coupled"]) > 0.4               # +0.104 instead of -0.423
+    assert ref["jk_Cv"] + sos["Cv_sampling"] > 10 * sos["Cv_coupled"]
