@@ -62,12 +62,13 @@ def algorithmic_flops_per_sample(A, N, P, Ar):
 
 # ----------------------------------------------------------------------------- CPU (reference arm)
 def _cpu_worker(args):
-    X, B, seed = args
+    X, B, seed = args[:3]
+    blas_threads = args[3] if len(args) > 3 else 1      # None: whatever the BLAS picks (the reference's single-job mode)
     from threadpoolctl import threadpool_limits
     from oracle import pimc_oracle as orc
     from pibronic_b200 import synthetic
     from pibronic_b200.model_io import VMK
-    with threadpool_limits(limits=1):
+    with threadpool_limits(limits=blas_threads):
         model = synthetic.model_c2()
         rho = synthetic.diagonal_of(model)
         vib_d = dict(A=A, N=N, E=model[VMK.E], w=model[VMK.w], L=model[VMK.G1], Q=model[VMK.G2])
@@ -242,8 +243,12 @@ def run_b200(args, rank, local_rank, world):
         achieved = flops * samples_per_s_kernel / 1e12
         cpu_procs = os.cpu_count() or 1
         cpu_rate, cpu_dt, cpu_mean = (None, None, None)
+        single_rate = None
         if world == 1 and not args.skip_cpu:
             cpu_rate, cpu_dt, cpu_mean = cpu_port_rate(cpu_procs)
+            # the reference's actual mode: ONE process (sbatch --ntasks=1, job_boss.py:314), BLAS threads left alone
+            dt1, _ = _cpu_worker((2000, 1000, 7, None))
+            single_rate = 2000 * P / dt1
         line = {
             "metric": "PIMC samples*beads/sec", "value": value, "unit": "samples*beads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -267,7 +272,9 @@ def run_b200(args, rank, local_rank, world):
             "cpu_baseline": {"value": cpu_rate, "unit": "samples*beads/s", "cores": cpu_procs, "kind": "port",
                              "sample": f"{cpu_procs} processes x {CPU_SAMPLES_PER_PROC} samples, numpy port of "
                                        f"block_compute_pm (oracle/pimc_oracle.py), 1 BLAS thread each, slowest shard "
-                                       f"{cpu_dt if cpu_dt is None else round(cpu_dt, 2)} s"},
+                                       f"{cpu_dt if cpu_dt is None else round(cpu_dt, 2)} s",
+                             "single_process_value": single_rate,
+                             "single_process_sample": "1 process x 2000 samples, default BLAS threads (the reference's one-job mode)"},
             "e2e": {"value": e2e_value, "unit": "samples*beads/s", "h2d_bytes_per_step": table_bytes,
                     "d2h_bytes_per_step": 4 * X * 8 + blocks * _cabi.NSUMS * 8, "steps": e2e_steps,
                     "call": "pbx_sample_eval_host (pinned, mapped host buffers: results written by the kernel, sums copied)"},

@@ -308,6 +308,11 @@ def test_plan_rejects_bad_models(case):
         _cabi.Plan(v["E"], -v["w"], v["L"], v["Q"], r["E"], r["w"], r["L"], 8, beta, 2e-4, device=-1)
     with pytest.raises(_cabi.PbxError, match="number of modes"):
         _cabi.Plan(v["E"], v["w"], v["L"], v["Q"], r["E"], r["w"][:-1], r["L"][:-1], 8, beta, 2e-4, device=-1)
+    # the consistent estimator needs g+- (PBX_FLAG_PM), the default exp(-tau V) builder and a register-resident shape
+    for flags in (_cabi.FLAG_M_TAU_PM, _cabi.FLAG_M_TAU_PM | _cabi.FLAG_PM | _cabi.FLAG_EIG_JACOBI,
+                  _cabi.FLAG_M_TAU_PM | _cabi.FLAG_PM | _cabi.FLAG_FORCE_GENERIC):
+        with pytest.raises(_cabi.PbxError, match="PBX_FLAG_M_TAU_PM"):
+            _cabi.Plan(v["E"], v["w"], v["L"], v["Q"], r["E"], r["w"], r["L"], 8, beta, 2e-4, flags=flags, device=-1)
 
 
 def test_plan_tables_match_oracle(case):
