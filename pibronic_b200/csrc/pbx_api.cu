@@ -319,6 +319,15 @@ int launch_mid_at(pbx_plan* p, const double* R, long long n, const BeadOutputs& 
     PBX_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     kb<<<(unsigned)((groups + MID_WARPS - 1) / MID_WARPS), MID_WARPS * 32, smem_b, st>>>(p->D, R, n, bo);
     PBX_CUDA(cudaGetLastError());
+    if (bo.m_mat) {   // X = -tau V  ->  M = exp(X), in place
+        const long long items = n * H.P;
+        const size_t smem_e = MID_WARPS * mid_expm_warp_doubles(AT) * sizeof(double);
+        auto ke = pbx_mid_expm_kernel<AT>;
+        PBX_CUDA(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+        ke<<<(unsigned)((items + MID_WARPS - 1) / MID_WARPS), MID_WARPS * 32, smem_e, st>>>(bo.m_mat, items);
+        PBX_CUDA(cudaGetLastError());
+        p->launches += 1;
+    }
     constexpr int spw = 32 / AT;
     const unsigned grid = (unsigned)((n + (long long)MID_WARPS * spw - 1) / ((long long)MID_WARPS * spw));
     const size_t smem_c = MID_WARPS * mid_chain_warp_doubles(AT) * sizeof(double);
@@ -449,7 +458,8 @@ int pbx_plan_create(const pbx_model* vib, const pbx_rho* rho, int32_t beads, dou
     size_t sm_need = GEN_WARPS * std::max(bead_warp_doubles(p->H.A, p->H.Ar, p->H.N),
                                           chain_warp_doubles(p->H.A, p->H.Ar)) * sizeof(double);
     if (p->H.A <= MID_AMAX)
-        sm_need = std::max(sm_need, MID_WARPS * mid_bead_warp_doubles(p->H.A, p->H.Ar, p->H.N) * sizeof(double));
+        sm_need = std::max({sm_need, MID_WARPS * mid_bead_warp_doubles(p->H.A, p->H.Ar, p->H.N) * sizeof(double),
+                            MID_WARPS * mid_expm_warp_doubles(p->H.A) * sizeof(double)});
     if (sm_need > 200 * 1024) { delete p; return fail(PBX_ERR_UNSUPPORTED, "A too large for the generic kernels"); }
     rc = upload_tables(p);
     if (rc != PBX_OK) { pbx_plan_destroy(p); return rc; }

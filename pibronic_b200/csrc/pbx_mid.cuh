@@ -4,13 +4,16 @@
 //
 //   pbx_mid_sample_kernel : thread per (sample, MODE PAIR) -- the N ring recurrences are independent,
 //                           so a 2400-sample chunk yields N/2 times more threads than thread-per-sample
-//   pbx_mid_bead_kernel   : one warp per MID_IB = 8 consecutive beads of a sample.  The coupling matrix
+//   pbx_mid_bead_kernel   : one warp per MID_IB = 8 consecutive beads of a sample: harmonic factors O (log space) and
+//                           X = -tau V.  The coupling matrix
 //                           V[bead][k] = e_off[k] + sum_n R_n l_off[n][k] + sum_{n<=m} q[n,m][k] R_n R_m is a
 //                           dense (8 beads x 325 features) x (325 x 78) contraction at c4: it runs on the FP64
 //                           tensor cores (mma.sync.m8n8k4.f64), 10 MMAs per 4 features, the table pre-tiled in
 //                           fragment order (210 KB, read as coalesced 256-byte rows from L1/L2).
-//                           exp(-tau V) uses a register-blocked 4x8-lane product (5 shared loads per
-//                           6 FMAs at A=12 instead of 2 per FMA).
+//   pbx_mid_expm_kernel   : one warp per (sample, bead): M = exp(X) in place, the four A x A products (+ squarings)
+//                           as mma.sync.m8n8k4.f64 tiles fed from shared memory (12 MMAs and 12 8-byte loads per
+//                           lane and product at A = 12).  Its own kernel so that neither part carries the other's
+//                           shared memory.
 //   pbx_mid_chain_kernel  : lane = (sample, row i): the rows of the three chained products live in
 //                           registers, M_p is broadcast from shared memory, floor(32/A) samples per warp.
 //
@@ -69,75 +72,86 @@ pbx_mid_sample_kernel(DevTables T, unsigned long long seed, long long first_samp
 }
 
 // ---------------------------------------------------------------------------------------------
-// register-blocked warp product of AT x AT matrices in shared memory (AT compile time), lanes as a
-// 4 x 8 grid: lane (li, lj) owns rows li + 4*ri (ri < RI) and columns lj + 8*cj (cj < CJ).
-// Out-of-range rows/columns are clamped (computed, never stored) so the inner loop has no predicates.
+// warp product of AT x AT matrices in shared memory (row-major, leading dimension AT) on the FP64 tensor cores:
+// mma.sync.m8n8k4 tiles, ceil(AT/8)^2 output tiles x ceil(AT/4) k-steps (12 MMAs at AT = 12).  With g = lane/4,
+// c = lane%4 a lane holds A[8 mt + g][4 ks + c], B[4 ks + c][8 nt + g] and C[8 mt + g][8 nt + 2c + {0,1}]; rows and
+// columns beyond AT are fed as zeros.  Per product a lane issues 2 ceil(AT/8) ceil(AT/4) 8-byte shared loads (12 at
+// AT = 12) -- the register-blocked vector form needed 60 and ran into the shared-memory bandwidth (ncu: L1 99 % busy).
 // ---------------------------------------------------------------------------------------------
 template <int AT> struct MidShape {
-    static constexpr int RI = (AT + 3) / 4, CJ = (AT + 7) / 8;
+    static constexpr int MT = (AT + 7) / 8, KS = (AT + 3) / 4;      // output tiles per dimension, k-steps
     static constexpr int AA = AT * (AT + 1) / 2, NT = (AA + 7) / 8, AA2 = AT * AT;   // NT: 8-wide mma tiles over the packed entries
 };
 
 template <int AT>
-struct LaneBlock {   // the entries of a matrix owned by one lane
-    double v[MidShape<AT>::RI][MidShape<AT>::CJ];
+struct MmaFrag {   // the entries of a matrix owned by one lane, accumulator layout
+    double v[MidShape<AT>::MT][MidShape<AT>::MT][2];
 };
 
-template <int AT>
-__device__ __forceinline__ void blk_matmul(const double* __restrict__ X, const double* __restrict__ Y, LaneBlock<AT>& C,
-                                           int li, int lj) {
-    constexpr int RI = MidShape<AT>::RI, CJ = MidShape<AT>::CJ;
-    int row[RI], col[CJ];
-#pragma unroll
-    for (int ri = 0; ri < RI; ++ri) row[ri] = min(li + 4 * ri, AT - 1) * AT;
-#pragma unroll
-    for (int cj = 0; cj < CJ; ++cj) col[cj] = min(lj + 8 * cj, AT - 1);
-#pragma unroll
-    for (int ri = 0; ri < RI; ++ri)
-#pragma unroll
-        for (int cj = 0; cj < CJ; ++cj) C.v[ri][cj] = 0.0;
-#pragma unroll
-    for (int k = 0; k < AT; ++k) {
-        double xv[RI], yv[CJ];
-#pragma unroll
-        for (int ri = 0; ri < RI; ++ri) xv[ri] = X[row[ri] + k];
-#pragma unroll
-        for (int cj = 0; cj < CJ; ++cj) yv[cj] = Y[k * AT + col[cj]];
-#pragma unroll
-        for (int ri = 0; ri < RI; ++ri)
-#pragma unroll
-            for (int cj = 0; cj < CJ; ++cj) C.v[ri][cj] = fma(xv[ri], yv[cj], C.v[ri][cj]);
-    }
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 template <int AT>
-__device__ __forceinline__ void blk_store(double* __restrict__ dst, const LaneBlock<AT>& C, int li, int lj) {
+__device__ __forceinline__ void mma_matmul(const double* __restrict__ X, const double* __restrict__ Y, MmaFrag<AT>& C, int lane) {
+    constexpr int MT = MidShape<AT>::MT, KS = MidShape<AT>::KS;
+    const int g = lane >> 2, c = lane & 3;
+    double a[MT][KS], b[MT][KS];
 #pragma unroll
-    for (int ri = 0; ri < MidShape<AT>::RI; ++ri)
+    for (int t = 0; t < MT; ++t)
 #pragma unroll
-        for (int cj = 0; cj < MidShape<AT>::CJ; ++cj) {
-            const int i = li + 4 * ri, j = lj + 8 * cj;
-            if (i < AT && j < AT) dst[i * AT + j] = C.v[ri][cj];
+        for (int ks = 0; ks < KS; ++ks) {
+            const int i = 8 * t + g, k = 4 * ks + c;
+            const bool ok = i < AT && k < AT;
+            a[t][ks] = ok ? X[i * AT + k] : 0.0;          // A[row i][k]
+            b[t][ks] = ok ? Y[k * AT + i] : 0.0;          // B[k][column i]
+        }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < MT; ++nt) {
+            C.v[mt][nt][0] = 0.0; C.v[mt][nt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) dmma_884(C.v[mt][nt][0], C.v[mt][nt][1], a[mt][ks], b[nt][ks]);
         }
 }
 
 template <int AT>
-__device__ __forceinline__ void blk_load(const double* __restrict__ src, LaneBlock<AT>& C, int li, int lj) {
+__device__ __forceinline__ void mma_store(double* __restrict__ dst, const MmaFrag<AT>& C, int lane) {
+    const int g = lane >> 2, c = lane & 3;
 #pragma unroll
-    for (int ri = 0; ri < MidShape<AT>::RI; ++ri)
+    for (int mt = 0; mt < MidShape<AT>::MT; ++mt)
 #pragma unroll
-        for (int cj = 0; cj < MidShape<AT>::CJ; ++cj)
-            C.v[ri][cj] = src[min(li + 4 * ri, AT - 1) * AT + min(lj + 8 * cj, AT - 1)];
+        for (int nt = 0; nt < MidShape<AT>::MT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = 8 * mt + g, j = 8 * nt + 2 * c + e;
+                if (i < AT && j < AT) dst[i * AT + j] = C.v[mt][nt][e];
+            }
+}
+
+template <int AT>
+__device__ __forceinline__ void mma_load(const double* __restrict__ src, MmaFrag<AT>& C, int lane) {
+    const int g = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MidShape<AT>::MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < MidShape<AT>::MT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = 8 * mt + g, j = 8 * nt + 2 * c + e;
+                C.v[mt][nt][e] = (i < AT && j < AT) ? src[i * AT + j] : 0.0;
+            }
 }
 
 // M = exp(X) (degree-12 Taylor in four products, scaling and squaring as in sym_expm); X in shared
 // memory is overwritten by its scaled copy; W0..W3 are AT*AT work matrices; the result is left in the
-// lane blocks `out` AND in shared memory at the returned pointer.
+// lane fragments `out` AND in shared memory at the returned pointer.
 template <int AT>
 __device__ __forceinline__ const double* warp_expm_at(double* X, double* W0, double* W1, double* W2, double* W3,
-                                                      LaneBlock<AT>& out, int lane) {
-    constexpr int RI = MidShape<AT>::RI, CJ = MidShape<AT>::CJ, AA2 = AT * AT;
-    const int li = lane >> 3, lj = lane & 7;
+                                                      MmaFrag<AT>& out, int lane) {
+    constexpr int MT = MidShape<AT>::MT, AA2 = AT * AT;
     double norm = 0.0;
     if (lane < AT) {
 #pragma unroll
@@ -150,62 +164,62 @@ __device__ __forceinline__ const double* warp_expm_at(double* X, double* W0, dou
     for (int e = lane; e < AA2; e += 32) X[e] *= scale;
     __syncwarp();
     // four-product degree-12 Taylor polynomial (pbx_device.cuh, namespace t12)
-    LaneBlock<AT> x1, x2, x3, y0, b;
-    auto diag = [&](int ri, int cj) { return (li + 4 * ri) == (lj + 8 * cj); };
-    blk_load<AT>(X, x1, li, lj);
-    blk_matmul<AT>(X, X, x2, li, lj);
-    blk_store<AT>(W0, x2, li, lj);          // W0 = X^2
+    MmaFrag<AT> x1, x2, x3, y0, b;
+    const int g = lane >> 2, c = lane & 3;
+    auto diag = [&](int mt, int nt, int e) { return (8 * mt + g) == (8 * nt + 2 * c + e); };
+#define PBX_FRAG_LOOP                                  \
+    _Pragma("unroll") for (int mt = 0; mt < MT; ++mt)  \
+    _Pragma("unroll") for (int nt = 0; nt < MT; ++nt)  \
+    _Pragma("unroll") for (int e = 0; e < 2; ++e)
+    mma_load<AT>(X, x1, lane);
+    mma_matmul<AT>(X, X, x2, lane);
+    mma_store<AT>(W0, x2, lane);            // W0 = X^2
     __syncwarp();
-    blk_matmul<AT>(X, W0, x3, li, lj);
-    blk_store<AT>(W1, x3, li, lj);          // W1 = X^3
-#pragma unroll
-    for (int ri = 0; ri < RI; ++ri)
-#pragma unroll
-        for (int cj = 0; cj < CJ; ++cj)
-            b.v[ri][cj] = fma(t12::c1, x3.v[ri][cj], fma(t12::c2, x2.v[ri][cj], t12::c3 * x1.v[ri][cj]));
-    blk_store<AT>(W2, b, li, lj);
+    mma_matmul<AT>(X, W0, x3, lane);
+    mma_store<AT>(W1, x3, lane);            // W1 = X^3
+    PBX_FRAG_LOOP b.v[mt][nt][e] = fma(t12::c1, x3.v[mt][nt][e], fma(t12::c2, x2.v[mt][nt][e], t12::c3 * x1.v[mt][nt][e]));
+    mma_store<AT>(W2, b, lane);
     __syncwarp();
-    blk_matmul<AT>(W1, W2, y0, li, lj);     // Y0 = X^3 (c1 X^3 + c2 X^2 + c3 X)
+    mma_matmul<AT>(W1, W2, y0, lane);       // Y0 = X^3 (c1 X^3 + c2 X^2 + c3 X)
     __syncwarp();                           // W2 is rewritten below
-#pragma unroll
-    for (int ri = 0; ri < RI; ++ri)
-#pragma unroll
-        for (int cj = 0; cj < CJ; ++cj) {
-            b.v[ri][cj] = y0.v[ri][cj] + fma(t12::c4, x3.v[ri][cj], fma(t12::c5, x2.v[ri][cj], t12::c6 * x1.v[ri][cj]));
-            out.v[ri][cj] = y0.v[ri][cj] + fma(t12::c7, x3.v[ri][cj], t12::c8 * x2.v[ri][cj]);
-        }
-    blk_store<AT>(W2, b, li, lj);
-    blk_store<AT>(W3, out, li, lj);
+    PBX_FRAG_LOOP {
+        b.v[mt][nt][e] = y0.v[mt][nt][e] + fma(t12::c4, x3.v[mt][nt][e], fma(t12::c5, x2.v[mt][nt][e], t12::c6 * x1.v[mt][nt][e]));
+        out.v[mt][nt][e] = y0.v[mt][nt][e] + fma(t12::c7, x3.v[mt][nt][e], t12::c8 * x2.v[mt][nt][e]);
+    }
+    mma_store<AT>(W2, b, lane);
+    mma_store<AT>(W3, out, lane);
     __syncwarp();
-    blk_matmul<AT>(W2, W3, out, li, lj);
-#pragma unroll
-    for (int ri = 0; ri < RI; ++ri)
-#pragma unroll
-        for (int cj = 0; cj < CJ; ++cj)
-            out.v[ri][cj] = out.v[ri][cj] + fma(t12::c9, y0.v[ri][cj], fma(t12::c10, x3.v[ri][cj], fma(0.5, x2.v[ri][cj], x1.v[ri][cj]))) +
-                            (diag(ri, cj) ? 1.0 : 0.0);
+    mma_matmul<AT>(W2, W3, out, lane);
+    PBX_FRAG_LOOP out.v[mt][nt][e] = out.v[mt][nt][e] +
+        fma(t12::c9, y0.v[mt][nt][e], fma(t12::c10, x3.v[mt][nt][e], fma(0.5, x2.v[mt][nt][e], x1.v[mt][nt][e]))) +
+        (diag(mt, nt, e) ? 1.0 : 0.0);
+#undef PBX_FRAG_LOOP
     __syncwarp();                           // all lanes are done reading W2, W3
     double* cur = W2;
     double* nxt = W3;
-    blk_store<AT>(cur, out, li, lj);
+    mma_store<AT>(cur, out, lane);
     __syncwarp();
     for (int q = 0; q < s; ++q) {
-        blk_matmul<AT>(cur, cur, out, li, lj);
-        blk_store<AT>(nxt, out, li, lj);
+        mma_matmul<AT>(cur, cur, out, lane);
+        mma_store<AT>(nxt, out, lane);
         __syncwarp();
         double* t = cur; cur = nxt; nxt = t;
     }
     return cur;
 }
 
-// shared memory (doubles) of one warp of the bead kernel
+// shared memory (doubles) of one warp of the V/O kernel: coordinate tile, a 2-bead staging tile, the log factors
 __host__ __device__ inline size_t mid_bead_warp_doubles(int A, int Ar, int N) {
-    size_t n = (size_t)(N + 1) * MID_RS + (size_t)MID_IB * A * A + 4 * (size_t)A * A + (size_t)MID_IB * (3 * A + Ar);
+    size_t n = (size_t)(N + 1) * MID_RS + 2 * (size_t)A * A + (size_t)MID_IB * (3 * A + Ar);
     return (n + 1) & ~(size_t)1;
 }
+// ... and of the exp kernel: X and four work matrices
+__host__ __device__ inline size_t mid_expm_warp_doubles(int A) { return 5 * (size_t)A * A; }
 
 // ---------------------------------------------------------------------------------------------
-// per-bead stage: one warp per MID_IB consecutive beads of one sample; AT = number of surfaces
+// per-bead stage, part 1: one warp per MID_IB consecutive beads of one sample; AT = number of surfaces.
+// Harmonic factors O (log space) and X = -tau V (written to out.m_mat, where part 2 turns it into exp(X) in place).
+// Small per-warp footprint (7 KB of shared memory at c4, no work matrices) -> 20 warps per SM.
 // ---------------------------------------------------------------------------------------------
 template <int AT>
 __global__ void __launch_bounds__(MID_WARPS * 32)
@@ -222,10 +236,8 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
     const int nb = min(MID_IB, P - p0);
     double* w = sm + (size_t)warp * mid_bead_warp_doubles(AT, Ar, N);
     double* Rt = w;                               // [N + 1][MID_RS]: beads p0 .. p0+MID_IB (ring closed); row N = ones
-    double* Xs = Rt + (size_t)(N + 1) * MID_RS;   // [MID_IB][AT][AT]
-    double* W0 = Xs + (size_t)MID_IB * AA2;       // 4 work matrices
-    double *W1 = W0 + AA2, *W2 = W1 + AA2, *W3 = W2 + AA2;
-    double* lall = W3 + AA2;                      // [MID_IB][3*AT + Ar] log factors
+    double* Xst = Rt + (size_t)(N + 1) * MID_RS;  // [2][AT][AT] staging for coalesced stores
+    double* lall = Xst + 2 * (size_t)AA2;         // [MID_IB][3*AT + Ar] log factors
     const int nl = 3 * AT + Ar;
     const double* Rx = R + (size_t)x * N * P;
     for (int e = lane; e < N * (MID_IB + 1); e += 32) {
@@ -237,50 +249,6 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
     if (lane < MID_RS) Rt[N * MID_RS + lane] = 1.0;
     __syncwarp();
     const size_t xp0 = (size_t)x * P + p0;
-
-    // ---- V for the 8 beads of the group on the FP64 tensor cores: V[bead][k] = sum_f feat_f(bead) coef[f][k] is an
-    //      (8 x K) x (K x AA) product, K = N(N+1)/2 + N + 1 features (R_n R_m, R_n, 1).  One mma.sync.m8n8k4 per
-    //      (4 features, 8 packed entries): lane (r = lane/4, c = lane%4) forms its A element -- feature 4 ks + c of
-    //      bead r -- with one multiply, the B fragments are coalesced 256-byte rows of the pre-tiled table.
-    if (out.v_mat || out.m_mat) {
-        constexpr int NT = MidShape<AT>::NT;
-        double acc[NT][2];
-#pragma unroll
-        for (int j = 0; j < NT; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
-        const int r = lane >> 2, c = lane & 3;
-        const double* qb = T.q_dmma + lane;
-        const double* Rr = Rt + r;
-#pragma unroll 2
-        for (int ks = 0; ks < T.KS; ++ks) {
-            const int f = __ldg(T.feat + 4 * ks + c);
-            const double a = Rr[(f & 0xffff) * MID_RS] * Rr[(f >> 16) * MID_RS];
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const double b = __ldg(qb + ((size_t)ks * NT + j) * 32);
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                             : "+d"(acc[j][0]), "+d"(acc[j][1]) : "d"(a), "d"(b));
-            }
-        }
-        // accumulator layout: lane holds V[bead r][k = 8 j + 2 c + e], e = 0, 1
-        if (r < nb) {
-#pragma unroll
-            for (int j = 0; j < NT; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int ij = __ldg(T.tri_ij + 8 * j + 2 * c + e);
-                    if (ij < 0) continue;
-                    const int i = ij >> 16, jj2 = ij & 0xffff;
-                    const double v = acc[j][e];
-                    if (out.v_mat) {
-                        out.v_mat[(xp0 + r) * AA2 + i * AT + jj2] = v;
-                        out.v_mat[(xp0 + r) * AA2 + jj2 * AT + i] = v;
-                    }
-                    Xs[(size_t)r * AA2 + i * AT + jj2] = v * T.neg_tau;
-                    Xs[(size_t)r * AA2 + jj2 * AT + i] = v * T.neg_tau;
-                }
-        }
-        __syncwarp();
-    }
 
     // ---- O factors in log space for the beads of the group at once; work items (set, surface)
     for (int it = lane; it < nl; it += 32) {
@@ -306,8 +274,6 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
         for (int jj = 0; jj < MID_IB; ++jj) lall[jj * nl + it] = dead ? -INFINITY : acc[jj];
     }
     __syncwarp();
-
-    const int li = lane >> 3, lj = lane & 7;
     for (int jj = 0; jj < nb; ++jj) {
         const size_t xp = xp0 + jj;
         const double* lv = lall + jj * nl;          // [3][AT] then [Ar]
@@ -325,13 +291,81 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
             if (out.lr) out.lr[xp * Ar + a] = lv[3 * AT + a] - logS;
             if (out.o_rho) out.o_rho[xp * Ar + a] = exp(lv[3 * AT + a] - logS);
         }
-        if (out.m_mat) {
-            LaneBlock<AT> m;
-            warp_expm_at<AT>(Xs + (size_t)jj * AA2, W0, W1, W2, W3, m, lane);
-            blk_store<AT>(out.m_mat + xp * AA2, m, li, lj);
-            __syncwarp();
+    }
+    if (!out.v_mat && !out.m_mat) return;
+
+    // ---- V for the 8 beads of the group on the FP64 tensor cores: V[bead][k] = sum_f feat_f(bead) coef[f][k] is an
+    //      (8 x K) x (K x AA) product, K = N(N+1)/2 + N + 1 features (R_n R_m, R_n, 1).  One mma.sync.m8n8k4 per
+    //      (4 features, 8 packed entries): lane (r = lane/4, c = lane%4) forms its A element -- feature 4 ks + c of
+    //      bead r -- with one multiply, the B fragments are coalesced 256-byte rows of the pre-tiled table.
+    constexpr int NT = MidShape<AT>::NT;
+    double acc[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+    const int r = lane >> 2, c = lane & 3;
+    const double* qb = T.q_dmma + lane;
+    const double* Rr = Rt + r;
+#pragma unroll 2
+    for (int ks = 0; ks < T.KS; ++ks) {
+        const int f = __ldg(T.feat + 4 * ks + c);
+        const double a = Rr[(f & 0xffff) * MID_RS] * Rr[(f >> 16) * MID_RS];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const double b = __ldg(qb + ((size_t)ks * NT + j) * 32);
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(acc[j][0]), "+d"(acc[j][1]) : "d"(a), "d"(b));
         }
     }
+    // accumulator layout: lane holds V[bead r][k = 8 j + 2 c + e], e = 0, 1.  Two beads at a time go through the staging
+    // tile as full symmetric matrices and leave as coalesced rows.
+    int ij[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) ij[j][e] = __ldg(T.tri_ij + 8 * j + 2 * c + e);
+    for (int pair = 0; 2 * pair < nb; ++pair) {
+        if ((r >> 1) == pair) {
+            double* dst = Xst + (size_t)(r & 1) * AA2;
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (ij[j][e] < 0) continue;
+                    const int i = ij[j][e] >> 16, jj2 = ij[j][e] & 0xffff;
+                    dst[i * AT + jj2] = acc[j][e];
+                    dst[jj2 * AT + i] = acc[j][e];
+                }
+        }
+        __syncwarp();
+        const int nbp = min(2, nb - 2 * pair);
+        for (int e = lane; e < nbp * AA2; e += 32) {
+            const double v = Xst[e];
+            if (out.v_mat) out.v_mat[(xp0 + 2 * pair) * AA2 + e] = v;
+            if (out.m_mat) out.m_mat[(xp0 + 2 * pair) * AA2 + e] = v * T.neg_tau;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-bead stage, part 2: m_mat[item] <- exp(m_mat[item]) in place, one warp per (sample, bead) matrix
+// ---------------------------------------------------------------------------------------------
+template <int AT>
+__global__ void __launch_bounds__(MID_WARPS * 32)
+pbx_mid_expm_kernel(double* __restrict__ m_mat, long long n_items) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int AA2 = AT * AT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * MID_WARPS + warp;
+    if (item >= n_items) return;
+    double* X = sm + (size_t)warp * mid_expm_warp_doubles(AT);
+    double *W0 = X + AA2, *W1 = W0 + AA2, *W2 = W1 + AA2, *W3 = W2 + AA2;
+    double* g = m_mat + (size_t)item * AA2;
+    for (int e = lane; e < AA2; e += 32) X[e] = g[e];
+    __syncwarp();
+    MmaFrag<AT> m;
+    warp_expm_at<AT>(X, W0, W1, W2, W3, m, lane);
+    mma_store<AT>(g, m, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
