@@ -174,6 +174,10 @@ def main():
                join(ex, "paper_1.5025058/alternate_rhos/displaced_D4_R1.json"), P=128, T=350.0, X=8, B=4, seed=15)
     # c4 in miniature: A=12, N=24 (large-A path), few beads
     write_case("c4mini_12x24", synthetic.model_c4(), None, P=8, T=300.0, X=4, B=2, seed=16)
+    # the shape of the reference's largest example model (artificial_systems/input_json/model_7x12.json, which itself has no
+    # inter-surface coupling): 7 surfaces x 12 modes with linear + quadratic coupling -> blocked kernels, odd A, padded MMA tiles
+    m712 = synthetic.coupled_model(7, 12, (0.02, 0.3), (0.5, 1.2), seed=23, quadratic=0.06)
+    write_case("syn_7x12", m712, None, P=20, T=300.0, X=8, B=4, seed=18)
     # c5: c2 model sampled from a different rho (the un-rotated diagonal model)
     rng_free = synthetic.coupled_model(4, 6, (0.14, 0.45), (10.3, 10.9), mixing=0.0, quadratic=0.0)
     write_case("c5_altrho", c2, synthetic.diagonal_of(rng_free), P=16, T=300.0, X=16, B=8, seed=17)
