@@ -41,7 +41,7 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-constexpr size_t kScratchTarget = (size_t)1 << 30;  // aim for <= 1 GiB of intermediates per chunk
+constexpr size_t kScratchTarget = (size_t)4 << 30;  // aim for <= 4 GiB of intermediates per chunk (the sampler kernel of the large-A path needs ~1e4 samples to fill the GPU)
 constexpr long long kFastCoordChunk = 4 * 148 * 2 * 128;  // samples per transposed-coordinate chunk: 4 full waves of CTAs
 
 // ---- per-block sums ------------------------------------------------------------------------
