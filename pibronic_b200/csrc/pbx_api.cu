@@ -324,7 +324,8 @@ int launch_mid_at(pbx_plan* p, const double* R, long long n, const BeadOutputs& 
         const size_t smem_e = MID_WARPS * mid_expm_warp_doubles(AT) * sizeof(double);
         auto ke = pbx_mid_expm_kernel<AT>;
         PBX_CUDA(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-        ke<<<(unsigned)((items + MID_WARPS - 1) / MID_WARPS), MID_WARPS * 32, smem_e, st>>>(bo.m_mat, items);
+        const long long grid_e = std::min<long long>((items + MID_WARPS - 1) / MID_WARPS, 148 * 5);   // persistent warps, 5 CTAs per SM
+        ke<<<(unsigned)grid_e, MID_WARPS * 32, smem_e, st>>>(bo.m_mat, items);
         PBX_CUDA(cudaGetLastError());
         p->launches += 1;
     }

@@ -29,6 +29,13 @@ constexpr int MID_RS = MID_IB + 2;  // row stride of the coordinate tile (even: 
 constexpr int MID_WARPS = 4;
 constexpr int MID_AMAX = 16;
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N_)); }
+
 // ---------------------------------------------------------------------------------------------
 // sampler: thread per (sample, mode pair); same Philox counters and arithmetic as the fused kernel's sampler phase
 // ---------------------------------------------------------------------------------------------
@@ -213,8 +220,8 @@ __host__ __device__ inline size_t mid_bead_warp_doubles(int A, int Ar, int N) {
     size_t n = (size_t)(N + 1) * MID_RS + 2 * (size_t)A * A + (size_t)MID_IB * (3 * A + Ar);
     return (n + 1) & ~(size_t)1;
 }
-// ... and of the exp kernel: X and four work matrices
-__host__ __device__ inline size_t mid_expm_warp_doubles(int A) { return 5 * (size_t)A * A; }
+// ... and of the exp kernel: X double-buffered and four work matrices
+__host__ __device__ inline size_t mid_expm_warp_doubles(int A) { return 6 * (size_t)A * A; }
 
 // ---------------------------------------------------------------------------------------------
 // per-bead stage, part 1: one warp per MID_IB consecutive beads of one sample; AT = number of surfaces.
@@ -348,7 +355,9 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-bead stage, part 2: m_mat[item] <- exp(m_mat[item]) in place, one warp per (sample, bead) matrix
+// per-bead stage, part 2: m_mat[item] <- exp(m_mat[item]) in place, one warp per (sample, bead) matrix.
+// Persistent warps with a grid stride: the next matrix is fetched with cp.async while the current one is
+// exponentiated (a warp that loaded its own matrix first sat on the HBM latency: long_scoreboard 7 per issue).
 // ---------------------------------------------------------------------------------------------
 template <int AT>
 __global__ void __launch_bounds__(MID_WARPS * 32)
@@ -356,16 +365,28 @@ pbx_mid_expm_kernel(double* __restrict__ m_mat, long long n_items) {
     extern __shared__ __align__(16) double sm[];
     constexpr int AA2 = AT * AT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long item = (long long)blockIdx.x * MID_WARPS + warp;
+    const long long stride = (long long)gridDim.x * MID_WARPS;
+    long long item = (long long)blockIdx.x * MID_WARPS + warp;
     if (item >= n_items) return;
-    double* X = sm + (size_t)warp * mid_expm_warp_doubles(AT);
-    double *W0 = X + AA2, *W1 = W0 + AA2, *W2 = W1 + AA2, *W3 = W2 + AA2;
-    double* g = m_mat + (size_t)item * AA2;
-    for (int e = lane; e < AA2; e += 32) X[e] = g[e];
-    __syncwarp();
-    MmaFrag<AT> m;
-    warp_expm_at<AT>(X, W0, W1, W2, W3, m, lane);
-    mma_store<AT>(g, m, lane);
+    double* base = sm + (size_t)warp * mid_expm_warp_doubles(AT);
+    double* Xb[2] = {base, base + AA2};
+    double *W0 = base + 2 * AA2, *W1 = W0 + AA2, *W2 = W1 + AA2, *W3 = W2 + AA2;
+    auto fetch = [&](long long it, double* dst) {
+        const double* g = m_mat + (size_t)it * AA2;
+        for (int e = lane; e < AA2; e += 32) cp_async8(dst + e, g + e);
+        cp_async_commit();
+    };
+    fetch(item, Xb[0]);
+    for (int b = 0; item < n_items; item += stride, b ^= 1) {
+        cp_async_wait<0>();
+        __syncwarp();
+        const long long nxt = item + stride;
+        if (nxt < n_items) fetch(nxt, Xb[b ^ 1]);
+        MmaFrag<AT> m;
+        warp_expm_at<AT>(Xb[b], W0, W1, W2, W3, m, lane);
+        mma_store<AT>(m_mat + (size_t)item * AA2, m, lane);
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,13 +397,6 @@ constexpr int MID_DEPTH = 4;   // beads in flight per warp
 __host__ __device__ inline size_t mid_chain_warp_doubles(int A) {
     return (size_t)MID_DEPTH * (32 / A) * ((size_t)A * A + 3 * A) + 32 * 3;
 }
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N_)); }
 
 template <int AT, bool PM>
 __global__ void __launch_bounds__(MID_WARPS * 32)
