@@ -12,7 +12,6 @@ import json
 import numpy as np
 
 from . import _cabi, constants, postprocessing as pp
-from .constants import boltzman
 from .pimc import BoxResultPM
 
 __all__ = ["add_harmonic_contribution", "basic_statistical_analysis", "basic_jackknife_analysis", "consistent_jackknife_analysis",

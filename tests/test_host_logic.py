@@ -4,7 +4,6 @@ import ctypes
 import json
 import os
 import re
-import shutil
 from os.path import join
 
 import numpy as np

@@ -3,7 +3,6 @@
     python tools/probe.py [X]
 """
 import sys
-import time
 from os.path import abspath, dirname
 
 sys.path.insert(0, dirname(dirname(abspath(__file__))))

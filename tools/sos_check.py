@@ -14,7 +14,6 @@ from os.path import abspath, dirname, join
 ROOT = dirname(dirname(abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import numpy as np
 import torch
 
 from oracle import pimc_oracle as orc          # model file readers only
