@@ -423,3 +423,36 @@ def test_estimator_on_cpu_sampler_agrees_with_reference_sampler():
     err = np.sqrt(r1.var() / X + r2.var() / X)
     assert abs(r1.mean() - r2.mean()) < 4 * err
     plan.close()
+
+
+def test_math_tables_header_is_what_the_generator_writes():
+    """csrc/pbx_math_tables.h (log / exp lookup tables of the device math) is generated, not edited"""
+    pytest.importorskip("mpmath")
+    import importlib.util
+    from os.path import dirname, join
+    root = dirname(dirname(__file__))
+    spec = importlib.util.spec_from_file_location("gen_math_tables", join(root, "tools", "gen_math_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    with open(join(root, "pibronic_b200", "csrc", "pbx_math_tables.h")) as fh:
+        assert fh.read() == gen.render()
+
+
+def test_four_product_exp_coefficients_match_taylor():
+    """the constants of namespace t12 (pbx_device.cuh) reproduce 1/k! for k = 0..12 when the four-product form is expanded"""
+    import re
+    from os.path import dirname, join
+    from numpy.polynomial import polynomial as npoly
+    with open(join(dirname(dirname(__file__)), "pibronic_b200", "csrc", "pbx_device.cuh")) as fh:
+        text = fh.read()
+    c = {int(k): float.fromhex(v) for k, v in re.findall(r"\bc(\d+) = (0x[0-9a-f.]+p[+-]\d+)", text)}
+    assert sorted(c) == list(range(1, 11))
+    x = np.array([0.0, 1.0])
+    x2, x3 = npoly.polymul(x, x), npoly.polymul(npoly.polymul(x, x), x)
+    y0 = npoly.polymul(x3, npoly.polyadd(c[1] * x3, npoly.polyadd(c[2] * x2, c[3] * x)))
+    a = npoly.polyadd(npoly.polyadd(y0, c[4] * x3), npoly.polyadd(c[5] * x2, c[6] * x))
+    b = npoly.polyadd(y0, npoly.polyadd(c[7] * x3, c[8] * x2))
+    total = npoly.polyadd(npoly.polymul(a, b), npoly.polyadd(npoly.polyadd(c[9] * y0, c[10] * x3), npoly.polyadd(0.5 * x2, npoly.polyadd(x, [1.0]))))
+    from math import factorial
+    want = np.array([1.0 / factorial(k) for k in range(13)])
+    assert len(total) == 13 and np.allclose(total, want, rtol=1e-13, atol=0)
