@@ -312,7 +312,7 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
     const int r = lane >> 2, c = lane & 3;
     const double* qb = T.q_dmma + lane;
     const double* Rr = Rt + r;
-#pragma unroll 2
+#pragma unroll 4
     for (int ks = 0; ks < T.KS; ++ks) {
         const int f = __ldg(T.feat + 4 * ks + c);
         const double a = Rr[(f & 0xffff) * MID_RS] * Rr[(f >> 16) * MID_RS];
@@ -464,14 +464,28 @@ pbx_mid_chain_kernel(DevTables T, const double* __restrict__ m_mat, const double
             for (int v = 0; v < NV; ++v)
 #pragma unroll
                 for (int j = 0; j < AT; ++j) acc[v][j] = 0.0;
+            if constexpr (AT % 2 == 0) {      // every slot starts 16-byte aligned: two elements of M per shared load
 #pragma unroll
-            for (int k = 0; k < AT; ++k)
+                for (int k = 0; k < AT; ++k)
 #pragma unroll
-                for (int j = 0; j < AT; ++j) {
-                    const double m = Mq[k * AT + j];
+                    for (int j = 0; j < AT; j += 2) {
+                        const double2 m = *reinterpret_cast<const double2*>(Mq + k * AT + j);
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) acc[v][j] = fma(Trow[v][k], m, acc[v][j]);
-                }
+                        for (int v = 0; v < NV; ++v) {
+                            acc[v][j] = fma(Trow[v][k], m.x, acc[v][j]);
+                            acc[v][j + 1] = fma(Trow[v][k], m.y, acc[v][j + 1]);
+                        }
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < AT; ++k)
+#pragma unroll
+                    for (int j = 0; j < AT; ++j) {
+                        const double m = Mq[k * AT + j];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) acc[v][j] = fma(Trow[v][k], m, acc[v][j]);
+                    }
+            }
 #pragma unroll
             for (int v = 0; v < NV; ++v)
 #pragma unroll
