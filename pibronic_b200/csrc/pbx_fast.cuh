@@ -77,6 +77,8 @@ struct FastLaunch {
     long long out_ld;
     double* mirror;          // optional second copy of the results, [4][mirror_ld]: mapped pinned HOST memory written
     long long mirror_ld;     // straight from the kernel (posted PCIe writes overlap the compute; no D2H pass afterwards)
+    long long ws_full_ctas;  // warp-specialised kernel: CTAs [0, ws_full_ctas) take 4 groups of 64 samples (whole waves),
+    int ws_tail_groups;      // the CTAs of the last, partial wave ws_tail_groups each (filled in by launch_ws_one)
 };
 
 // MODE_REDO: MODE_SAMPLE restricted to the samples the warp-specialised kernel (pbx_fast_ws.cuh) flagged with

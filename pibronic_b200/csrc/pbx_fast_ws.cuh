@@ -104,12 +104,20 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
     const int P = T.P;
     const int n_stage = (P + WS_TB - 1) / WS_TB;
     const uint2 key = make_uint2((uint32_t)L.seed, (uint32_t)(L.seed >> 32));
-    const long long cta_first = (long long)blockIdx.x * WS_CONS;
+    // samples travel in groups of 64 (two producer warps + two consumer warps with their own barriers).  CTAs of the
+    // complete waves take four groups; the last, partial wave is spread over all SMs with fewer groups per CTA -- the
+    // warps of an absent group leave at once and the remaining ones have the schedulers to themselves
+    const long long cta = blockIdx.x;
+    const bool tail = cta >= L.ws_full_ctas;
+    const long long first_group = tail ? 4 * L.ws_full_ctas + (cta - L.ws_full_ctas) * L.ws_tail_groups : 4 * cta;
+    const int n_groups = tail ? L.ws_tail_groups : WS_GROUPS;
+    const long long cta_first = 64 * first_group;
 
     if (tid < WS_PROD) {
         // ------------------------------------------------------------------ producer
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PBX_WS_REG_PROD));
         const int g = tid / WS_GROUP_PROD, t = tid - g * WS_GROUP_PROD;
+        if (g >= n_groups || cta_first + 64 * g >= L.n_samples) return;
         int col[WS_SPT];
         unsigned long long gidx[WS_SPT];
 #pragma unroll
@@ -148,6 +156,7 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
     // ---------------------------------------------------------------------- consumer
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(PBX_WS_REG_CONS));
     const int c = tid - WS_PROD, g = c >> 6;
+    if (g >= n_groups || cta_first + 64 * g >= L.n_samples) return;
     long long x = cta_first + c;
     const bool live = x < L.n_samples;
     if (!live) x = L.n_samples - 1;
@@ -245,8 +254,15 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
 }
 
 template <int A, int N, int AR, bool PM, bool SHARE, bool MTAU = false>
-cudaError_t launch_ws_one(const FastTables<A, N, AR>& T, const FastLaunch& L, cudaStream_t stream) {
-    const long long blocks = (L.n_samples + WS_CONS - 1) / WS_CONS;
+cudaError_t launch_ws_one(const FastTables<A, N, AR>& T, const FastLaunch& L_in, cudaStream_t stream) {
+    FastLaunch L = L_in;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long groups = (L.n_samples + 63) / 64;
+    L.ws_full_ctas = (groups / WS_GROUPS) / sms * sms;                      // one CTA per SM: whole waves
+    const long long rest = groups - WS_GROUPS * L.ws_full_ctas;
+    L.ws_tail_groups = (int)std::min<long long>(WS_GROUPS, std::max<long long>(1, (rest + sms - 1) / sms));
+    const long long blocks = L.ws_full_ctas + (rest + L.ws_tail_groups - 1) / L.ws_tail_groups;
     constexpr size_t smem = ws_smem_bytes<N>();
     auto kernel = pbx_fast_ws_kernel<A, N, AR, PM, SHARE, MTAU>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
