@@ -40,7 +40,7 @@ X_PER_GPU = 1_000_000
 BLOCK_SIZE = 10_000
 CPU_SAMPLES_PER_PROC = 4000   # bounded CPU sample: about 3 s per process and step
 CPU_BLOCK = 1000
-NCU_DRAM_BYTES_PER_LAUNCH = 79872 + 77056   # from the committed ncu capture of the fused kernel, 1e6 samples per launch
+NCU_DRAM_BYTES_PER_LAUNCH = 80640 + 194816   # from the committed ncu capture of the fused kernel, 1e6 samples per launch
 WORKLOAD = (f"c2: synthetic A={A} N={N} P={P} lin+quad coupling, T={T_KELVIN:.0f}K, PM path, "
             f"X={X_PER_GPU:.0e} samples/GPU/step in blocks of {BLOCK_SIZE}")
 
