@@ -66,8 +66,19 @@ enum {
                                        /* formulation); default is a scaling-and-squaring exp(-tau V)      */
     PBX_FLAG_FORCE_GENERIC  = 1u << 4, /* never use the register-resident small-A kernels                 */
     PBX_FLAG_NO_SCALING     = 1u << 5, /* skip the per-bead S scaling (golden test of the reference)       */
-    PBX_FLAG_NO_WARPSPEC    = 1u << 6  /* fused sampler+estimator on the one-role kernel instead of the        */
+    PBX_FLAG_NO_WARPSPEC    = 1u << 6, /* fused sampler+estimator on the one-role kernel instead of the        */
                                        /* producer/consumer (warp-specialised) one; same results bit for bit  */
+    PBX_FLAG_NO_FUSED_DMMA  = 1u << 7, /* 2 <= A <= 16 without a register-resident kernel: the blocked kernels   */
+                                       /* through HBM scratch instead of the fused one-launch tensor-core kernel  */
+    PBX_FLAG_PREFER_DMMA    = 1u << 8  /* use the fused tensor-core kernel even where a register-resident one exists */
+};
+
+/* which kernel family a plan runs on (pbx_plan_kernel_path) */
+enum {
+    PBX_PATH_GENERIC    = 0,  /* any A: warp per (sample, bead) + warp per sample, through HBM scratch          */
+    PBX_PATH_REGISTER   = 1,  /* listed small shapes: one sample per thread, everything in registers            */
+    PBX_PATH_BLOCKED    = 2,  /* A <= 16: four blocked kernels through HBM scratch (round-1 large-A path)       */
+    PBX_PATH_FUSED_DMMA = 3   /* 2 <= A <= 16: one launch, one warp per sample, FP64 tensor cores, no scratch   */
 };
 
 /* coupled (vibronic) model: pibronic `coupled_model.json` arrays as loaded by ModelClass.load_model */
@@ -112,6 +123,8 @@ int pbx_plan_destroy(pbx_plan *plan);
 int64_t pbx_plan_table(const pbx_plan *plan, const char *name, double *out, int64_t count);
 /* 1 if the plan runs on a register-resident small-A kernel, 0 if on the generic kernels */
 int pbx_plan_is_fast(const pbx_plan *plan);
+/* PBX_PATH_* of the kernels the fused / coordinate entry points of this plan launch */
+int pbx_plan_kernel_path(const pbx_plan *plan);
 /* number of kernel launches issued through this plan so far */
 int64_t pbx_plan_launch_count(const pbx_plan *plan);
 /* bytes of kernel parameters (the model tables of the register-resident kernels travel this way) sent host->device

@@ -21,6 +21,9 @@ FLAG_EIG_JACOBI = 1 << 3
 FLAG_FORCE_GENERIC = 1 << 4
 FLAG_NO_SCALING = 1 << 5
 FLAG_NO_WARPSPEC = 1 << 6
+FLAG_NO_FUSED_DMMA = 1 << 7
+FLAG_PREFER_DMMA = 1 << 8
+PATH_GENERIC, PATH_REGISTER, PATH_BLOCKED, PATH_FUSED_DMMA = 0, 1, 2, 3
 NSUMS = 8
 SUM_NAMES = ("r", "r_plus", "r_minus", "r_sq", "d1", "d2", "d1_sq", "d2_sq")
 NSTATS = 10
@@ -67,6 +70,7 @@ def lib():
         "pbx_plan_destroy": (C.c_int, [vp]),
         "pbx_plan_table": (i64, [vp, C.c_char_p, _dp, i64]),
         "pbx_plan_is_fast": (C.c_int, [vp]),
+        "pbx_plan_kernel_path": (C.c_int, [vp]),
         "pbx_plan_launch_count": (i64, [vp]),
         "pbx_plan_launch_param_bytes": (i64, [vp]),
         "pbx_sample_eval_dev": (C.c_int, [vp, u64, i64, i64, vp, vp]),
@@ -92,7 +96,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ("pbx_abi_version", "pbx_last_error", "pbx_device_count", "pbx_plan_create", "pbx_plan_destroy",
-                    "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_launch_count", "pbx_plan_launch_param_bytes", "pbx_sample_eval_dev",
+                    "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_kernel_path", "pbx_plan_launch_count", "pbx_plan_launch_param_bytes", "pbx_sample_eval_dev",
                     "pbx_sample_eval_host", "pbx_eval_coords_dev", "pbx_eval_coords_host", "pbx_sample_coords_dev",
                     "pbx_eval_stages_dev", "pbx_chain_trace_dev", "pbx_block_sums_dev", "pbx_stats_dev", "pbx_stats_host",
                     "pbx_stats_last", "pbx_math_probe_dev", "pbx_fp64_peak_tflops", "pbx_fp64_peak_tflops_kind")
@@ -175,6 +179,11 @@ class Plan:
     @property
     def is_fast(self):
         return bool(lib().pbx_plan_is_fast(self._handle))
+
+    @property
+    def kernel_path(self):
+        """PATH_GENERIC / PATH_REGISTER / PATH_BLOCKED / PATH_FUSED_DMMA"""
+        return int(lib().pbx_plan_kernel_path(self._handle))
 
     @property
     def launch_count(self):

@@ -27,6 +27,9 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
     os.environ.get("PBX_EXTRA_NVCC_FLAGS", "").split()
 
 
+BIG_SURFACES = range(2, 17)     # keep in step with PBX_BIG_LIST in csrc/pbx_api.cu
+
+
 def shapes():
     with open(join(CSRC, "shapes.def")) as fh:
         return [tuple(int(v) for v in m.groups())
@@ -66,6 +69,9 @@ def build(force=False, verbose=False):
         obj = join(OBJ_DIR, f"pbx_fast_{A}_{N}_{AR}.o")
         jobs.append((obj, [NVCC, *ARCH, *CFLAGS, f"-DPBX_A={A}", f"-DPBX_N={N}", f"-DPBX_AR={AR}",
                            "-c", join(CSRC, "pbx_fast_inst.cu"), "-o", obj]))
+    for A in BIG_SURFACES:      # fused large-A kernel, one translation unit per number of surfaces
+        obj = join(OBJ_DIR, f"pbx_big_{A}.o")
+        jobs.append((obj, [NVCC, *ARCH, *CFLAGS, f"-DPBX_BIG_AT={A}", "-c", join(CSRC, "pbx_big_inst.cu"), "-o", obj]))
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
         logs = list(pool.map(lambda job: _run(job[1]), jobs))
     if verbose:

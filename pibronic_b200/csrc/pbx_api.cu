@@ -7,11 +7,27 @@
 #include <string>
 #include <vector>
 
+#include "pbx_big.cuh"
 #include "pbx_fast.cuh"
 #include "pbx_generic.cuh"
 #include "pbx_mid.cuh"
 
 using namespace pbx;
+
+namespace pbx {
+#define PBX_BIG_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#define PBX_BIG_DECL(A_) extern const BigLauncher big_launcher_##A_;
+PBX_BIG_LIST(PBX_BIG_DECL)
+#undef PBX_BIG_DECL
+BigLauncher find_big_kernel(int A) {
+    switch (A) {
+#define PBX_BIG_CASE(A_) case A_: return big_launcher_##A_;
+        PBX_BIG_LIST(PBX_BIG_CASE)
+#undef PBX_BIG_CASE
+    }
+    return nullptr;
+}
+}  // namespace pbx
 
 namespace {
 
@@ -217,6 +233,11 @@ struct pbx_plan {
     DevTables D{};
     const FastKernelEntry* fast = nullptr;
     std::vector<unsigned char> fast_tables;
+    BigLauncher big = nullptr;       // fused large-A kernel (pbx_big.cuh), null if the shape is not eligible
+    BigParams B{};
+    double* big_tab = nullptr;
+    size_t big_smem = 0;
+    int sms = 148;
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     void* io = nullptr;  // device staging for the *_host entry points
@@ -298,6 +319,51 @@ int upload_dmma_tables(pbx_plan* p) {
     PBX_CUDA(cudaMemcpy(p->dev_int_tables, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice));
     p->D.q_dmma = dq; p->D.feat = p->dev_int_tables; p->D.tri_ij = p->dev_int_tables + 4 * KS;
     p->D.KS = KS; p->D.NT = NT;
+    return PBX_OK;
+}
+
+// flat constant table of the fused large-A kernel (BigParams::tab) + its launch parameters
+int upload_big_tables(pbx_plan* p) {
+    const HostTables& H = p->H;
+    const int A = H.A, Ar = H.Ar, N = H.N;
+    std::vector<double> flat;
+    BigParams& B = p->B;
+    B.o_al = (int)flat.size();
+    for (int v = 0; v < 4; ++v) for (int n = 0; n < N; ++n) flat.push_back(-0.25 * H.tanh_half[v * N + n]);
+    B.o_ga = (int)flat.size();
+    for (int v = 0; v < 4; ++v) for (int n = 0; n < N; ++n) flat.push_back(-0.25 * H.coth_half[v * N + n]);
+    B.o_d2v = (int)flat.size();
+    for (int i = 0; i < A * N; ++i) flat.push_back(2.0 * H.d_vib[i]);
+    B.o_d2r = (int)flat.size();
+    for (int i = 0; i < Ar * N; ++i) flat.push_back(2.0 * H.d_rho[i]);
+    B.o_lpref = (int)flat.size();
+    flat.insert(flat.end(), H.logpref.begin(), H.logpref.end());
+    B.o_lprho = (int)flat.size();
+    flat.insert(flat.end(), H.logpref_rho.begin(), H.logpref_rho.end());
+    B.o_drho = (int)flat.size();
+    flat.insert(flat.end(), H.d_rho.begin(), H.d_rho.end());
+    B.tab_doubles = (int)flat.size();
+    p->big_smem = big_smem_bytes(A, p->pm, N, Ar, B.tab_doubles);
+    int max_smem = 0;
+    PBX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+    PBX_CUDA(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
+    if (p->big_smem > (size_t)max_smem) { p->big = nullptr; return PBX_OK; }   // falls back to the blocked kernels
+    PBX_CUDA(cudaMalloc((void**)&p->big_tab, flat.size() * sizeof(double)));
+    PBX_CUDA(cudaMemcpy(p->big_tab, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+    B.tab = p->big_tab;
+    B.Ar = Ar; B.N = N; B.P = H.P; B.n_rho_eval = H.n_rho_eval; B.KS = p->D.KS; B.neg_tau = -H.tau[0];
+    B.wcum = p->D.wcum; B.q_dmma = p->D.q_dmma; B.feat = p->D.feat; B.tri_ij = p->D.tri_ij; B.samp = p->D.samp;
+    return PBX_OK;
+}
+
+// one launch of the fused large-A kernel: R == nullptr draws the coordinates on-chip (needs N <= BIG_NMAX_SAMPLER)
+int launch_big(pbx_plan* p, const double* R, uint64_t seed, long long first, long long n, double* out4, long long out_ld,
+               double* mirror, long long mirror_ld, cudaStream_t st) {
+    BigParams B = p->B;
+    B.R = R; B.seed = seed; B.first_sample = first; B.n_samples = n; B.out4 = out4; B.out_ld = out_ld;
+    B.mirror = mirror; B.mirror_ld = mirror_ld;
+    PBX_CUDA(p->big(B, p->pm, R ? BIG_COORDS : BIG_SAMPLE, p->big_smem, p->sms, st));
+    p->launches += 1;
     return PBX_OK;
 }
 
@@ -467,6 +533,15 @@ int pbx_plan_create(const pbx_model* vib, const pbx_rho* rho, int32_t beads, dou
     if (p->H.A <= MID_AMAX) {
         rc = upload_dmma_tables(p);
         if (rc != PBX_OK) { pbx_plan_destroy(p); return rc; }
+        // fused large-A kernel: shapes without a register-resident kernel (or on request), default M builder, scaled
+        const bool want_big = (!p->fast || (flags & PBX_FLAG_PREFER_DMMA)) && !(flags & PBX_FLAG_FORCE_GENERIC) &&
+                              !(flags & PBX_FLAG_NO_FUSED_DMMA) && !p->jacobi && p->scale && !p->mtau && p->H.Ar <= BIG_ARMAX;
+        if (want_big) p->big = find_big_kernel(p->H.A);
+        if (p->big) {
+            rc = upload_big_tables(p);
+            if (rc != PBX_OK) { pbx_plan_destroy(p); return rc; }
+        }
+        if (p->big) p->fast = nullptr;
     }
     e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { pbx_plan_destroy(p); return cuda_fail(e, "cudaStreamCreate"); }
@@ -482,6 +557,7 @@ int pbx_plan_destroy(pbx_plan* p) {
     if (p->dev_tables) cudaFree(p->dev_tables);
     if (p->dev_int_tables) cudaFree(p->dev_int_tables);
     if (p->dmma_tables) cudaFree(p->dmma_tables);
+    if (p->big_tab) cudaFree(p->big_tab);
     if (p->scratch) cudaFree(p->scratch);
     if (p->io) cudaFree(p->io);
     if (p->stat_partials) cudaFree(p->stat_partials);
@@ -511,9 +587,16 @@ int64_t pbx_plan_table(const pbx_plan* p, const char* name, double* out, int64_t
 }
 
 int pbx_plan_is_fast(const pbx_plan* p) { return (p && p->fast) ? 1 : 0; }
+int pbx_plan_kernel_path(const pbx_plan* p) {
+    if (!p) return PBX_ERR_ARG;
+    if (p->fast) return PBX_PATH_REGISTER;
+    if (p->big) return PBX_PATH_FUSED_DMMA;
+    return use_mid_path(p) ? PBX_PATH_BLOCKED : PBX_PATH_GENERIC;
+}
 int64_t pbx_plan_launch_count(const pbx_plan* p) { return p ? p->launches : 0; }
 int64_t pbx_plan_launch_param_bytes(const pbx_plan* p) {
     if (!p) return 0;
+    if (p->big) return (int64_t)sizeof(BigParams);
     return p->fast ? (int64_t)(p->fast->table_bytes + sizeof(FastLaunch)) : (int64_t)sizeof(DevTables);
 }
 
@@ -535,6 +618,22 @@ int sample_eval_impl(pbx_plan* p, uint64_t seed, int64_t first_sample, int64_t n
         }
         PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_SAMPLE, p->pm, p->jacobi, p->H.rho_shares_vib, p->mtau, st));
         p->launches += 1;
+        return PBX_OK;
+    }
+    if (p->big && p->H.N <= BIG_NMAX_SAMPLER)      // sampler fused in: no scratch at all
+        return launch_big(p, nullptr, seed, first_sample, n, out4, n, mirror, mirror_ld, st);
+    if (p->big) {                                  // more modes than lanes: coordinates through a scratch buffer, in chunks
+        const size_t coords = (size_t)p->H.N * p->H.P;
+        const long long chunk = std::min<long long>(n, std::max<long long>(1, (long long)(kScratchTarget / (coords * sizeof(double)))));
+        int rc = ensure(&p->scratch, &p->scratch_bytes, (size_t)chunk * coords * sizeof(double));
+        if (rc != PBX_OK) return rc;
+        for (long long off = 0; off < n; off += chunk) {
+            const long long m = std::min<long long>(chunk, n - off);
+            rc = launch_sample_coords(p, seed, first_sample + off, m, (double*)p->scratch, nullptr, st);
+            if (rc != PBX_OK) return rc;
+            rc = launch_big(p, (const double*)p->scratch, 0, 0, m, out4 + off, n, mirror ? mirror + off : nullptr, mirror_ld, st);
+            if (rc != PBX_OK) return rc;
+        }
         return PBX_OK;
     }
     const long long chunk = generic_chunk(p, n, true);
@@ -600,6 +699,7 @@ int pbx_eval_coords_dev(pbx_plan* p, const double* R, int64_t n, double* out4, v
         }
         return PBX_OK;
     }
+    if (p->big) return launch_big(p, R, 0, 0, n, out4, n, nullptr, 0, st);      // reads the caller's R in place
     const long long chunk = generic_chunk(p, n, false);
     int rc = ensure(&p->scratch, &p->scratch_bytes, (size_t)chunk * generic_doubles_per_sample(H) * sizeof(double));
     if (rc != PBX_OK) return rc;
@@ -698,7 +798,7 @@ int pbx_sample_eval_host(pbx_plan* p, uint64_t seed, int64_t first_sample, int64
     if (first_sample < 0) return fail(PBX_ERR_ARG, "first_sample < 0");
     const size_t rows = p->pm ? 4 : 2;
     // pinned + mapped host buffer and a register-resident kernel: the kernel writes the host rows itself
-    double* mirror = p->fast ? mapped_alias(out4_host, ((rows - 1) * (size_t)ld_host + (size_t)n) * sizeof(double)) : nullptr;
+    double* mirror = (p->fast || p->big) ? mapped_alias(out4_host, ((rows - 1) * (size_t)ld_host + (size_t)n) * sizeof(double)) : nullptr;
     rc = sample_eval_impl(p, seed, first_sample, n, out_dev, mirror, ld_host, p->own_stream);
     if (rc != PBX_OK) return rc;
     if (sums_host) {

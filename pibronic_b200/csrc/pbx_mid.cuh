@@ -20,6 +20,7 @@
 // Reference: /root/reference/pibronic/pimc/pimc.py:1087-1129 (O), 1076-1084 (S), 1139-1187 (V, M),
 // 1194-1209 (chain), 1132-1136 (rho).
 #pragma once
+#include "pbx_dmma.cuh"
 #include "pbx_generic.cuh"
 
 namespace pbx {
@@ -85,20 +86,12 @@ pbx_mid_sample_kernel(DevTables T, unsigned long long seed, long long first_samp
 // columns beyond AT are fed as zeros.  Per product a lane issues 2 ceil(AT/8) ceil(AT/4) 8-byte shared loads (12 at
 // AT = 12) -- the register-blocked vector form needed 60 and ran into the shared-memory bandwidth (ncu: L1 99 % busy).
 // ---------------------------------------------------------------------------------------------
-template <int AT> struct MidShape {
-    static constexpr int MT = (AT + 7) / 8, KS = (AT + 3) / 4;      // output tiles per dimension, k-steps
-    static constexpr int AA = AT * (AT + 1) / 2, NT = (AA + 7) / 8, AA2 = AT * AT;   // NT: 8-wide mma tiles over the packed entries
-};
 
 template <int AT>
 struct MmaFrag {   // the entries of a matrix owned by one lane, accumulator layout
     double v[MidShape<AT>::MT][MidShape<AT>::MT][2];
 };
 
-__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 template <int AT>
 __device__ __forceinline__ void mma_matmul(const double* __restrict__ X, const double* __restrict__ Y, MmaFrag<AT>& C, int lane) {

@@ -16,6 +16,8 @@ VARIANTS = {
     "jacobi": _cabi.FLAG_EIG_JACOBI,
     "generic": _cabi.FLAG_FORCE_GENERIC,
     "generic_jacobi": _cabi.FLAG_FORCE_GENERIC | _cabi.FLAG_EIG_JACOBI,
+    "fused_dmma": _cabi.FLAG_PREFER_DMMA,        # one-launch tensor-core kernel also where a register-resident one exists
+    "blocked": _cabi.FLAG_NO_FUSED_DMMA,         # round-1 large-A path through HBM scratch
 }
 
 
@@ -175,7 +177,7 @@ def test_device_sampler_matches_its_cpu_restatement(cuda, case):
     plan.close()
 
 
-@pytest.mark.parametrize("variant", ["default", "generic"])
+@pytest.mark.parametrize("variant", ["default", "generic", "fused_dmma"])
 def test_fused_kernel_equals_sampler_then_estimator(cuda, case, variant):
     """the fused sampler+estimator gives what the estimator gives on the coordinates the sampler kernel
     reports for the same Philox counters -- and both match the oracle on those coordinates"""
