@@ -28,12 +28,28 @@
 #ifndef PBX_BIG_WARPS
 #define PBX_BIG_WARPS 8
 #endif
+#ifndef PBX_BIG_PAIRING
+#define PBX_BIG_PAIRING 0      // which warps alternate: 0 = (w, w + BIG_WARPS/2), 1 = (2p, 2p + 1)
+#endif
+#ifndef PBX_BIG_CH
+#define PBX_BIG_CH 4           // k-steps per stage of the coefficient ring
+#endif
+#ifndef PBX_BIG_STAGES
+#define PBX_BIG_STAGES 3
+#endif
+#ifndef PBX_BIG_PINGPONG
+#define PBX_BIG_PINGPONG 0     // 1: the two warps of a scheduler alternate phases (named barriers), see the kernel
+#endif
 
 namespace pbx {
 
 constexpr int BIG_G = 16;            // beads per group: two m8 row tiles of the coupling contraction
 constexpr int BIG_RS = BIG_G + 2;    // row stride of the coordinate tile (17 beads: the group and the next one)
-constexpr int BIG_WARPS = PBX_BIG_WARPS;
+constexpr int BIG_WARPS = PBX_BIG_WARPS, BIG_CH = PBX_BIG_CH, BIG_STAGES = PBX_BIG_STAGES;
+#ifndef PBX_BIG_TABLE_COPIES
+#define PBX_BIG_TABLE_COPIES 16
+#endif
+constexpr int BIG_TABLE_COPIES = PBX_BIG_TABLE_COPIES;   // identical copies of the coefficient table at different addresses (L2 slices)
 constexpr int BIG_AMAX = 16, BIG_ARMAX = 32, BIG_NMAX_SAMPLER = 32;
 
 enum { BIG_COORDS = 0, BIG_SAMPLE = 1 };
@@ -47,7 +63,8 @@ struct BigParams {
     int tab_doubles;
     int o_al, o_ga, o_d2v, o_d2r, o_lpref, o_lprho, o_drho;
     const double* wcum;      // [Ar]
-    const double* q_dmma;    // [KS][NT][32] coupling coefficients in mma fragment order (DevTables::q_dmma)
+    const double* q_dmma;    // [BIG_TABLE_COPIES][KS][NT][32] coupling coefficients in mma fragment order (DevTables::q_dmma)
+    long long q_copy_stride; // doubles between the copies
     const int* feat;         // [4 KS]
     const int* tri_ij;       // [8 NT]
     const double* samp;      // [P][N][3]
@@ -86,6 +103,39 @@ __host__ __device__ inline BigLayout big_layout(int A, int NV, int N, int Ar) {
     return L;
 }
 
+// doubles of CTA-shared tables in front of the per-warp regions: the constant table and the feature offsets [4 KS] (ints)
+__host__ __device__ inline int big_cta_doubles(int tab_doubles, int KS, int NT) {
+    return big_even(tab_doubles) + big_even(2 * KS) + BIG_STAGES * BIG_CH * NT * 32 + 2 * BIG_STAGES;
+}
+
+// ---- mbarrier / TMA bulk-copy primitives (shared::cta)
+__device__ __forceinline__ uint32_t big_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void big_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(big_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void big_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(big_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void big_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(big_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void big_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "BIG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra BIG_DONE;\n"
+        "bra BIG_WAIT;\n"
+        "BIG_DONE:\n"
+        "}\n" ::"r"(big_smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`; 16-byte aligned addresses and size
+__device__ __forceinline__ void big_bulk_copy(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(big_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(big_smem_u32(bar)) : "memory");
+}
+
 template <int AT> struct BigFrag { double v[MidShape<AT>::MT][MidShape<AT>::MT][2]; };   // accumulator layout
 template <int AT> struct BigOp { double v[MidShape<AT>::MT][MidShape<AT>::KS]; };        // operand layout (A == B^T for symmetric matrices)
 
@@ -95,11 +145,15 @@ __device__ __forceinline__ void big_prod(const BigOp<AT>& X, const BigOp<AT>& Y,
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < MT; ++nt) {
-            C.v[mt][nt][0] = 0.0; C.v[mt][nt][1] = 0.0;
+        for (int nt = 0; nt < MT; ++nt) { C.v[mt][nt][0] = 0.0; C.v[mt][nt][1] = 0.0; }
+    // k-step outermost: consecutive tensor instructions write different accumulator tiles (a dependent DMMA cannot
+    // issue until the previous one has left the pipe)
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) dmma_884(C.v[mt][nt][0], C.v[mt][nt][1], X.v[mt][ks], Y.v[nt][ks]);
-        }
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < MT; ++nt) dmma_884(C.v[mt][nt][0], C.v[mt][nt][1], X.v[mt][ks], Y.v[nt][ks]);
 }
 
 // operand fragment of a matrix in shared memory (row stride LDM): lane (g, c) holds M[8 t + g][4 ks + c]
@@ -134,7 +188,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1)
 pbx_big_kernel(const BigParams Q) {
     extern __shared__ __align__(16) double sm[];
     using Sh = MidShape<AT>;
-    constexpr int NV = PM ? 3 : 1, MT = Sh::MT, KSA = Sh::KS, NT = Sh::NT, AA = Sh::AA;
+    constexpr int NV = PM ? 3 : 1, MT = Sh::MT, KSA = Sh::KS, NT = Sh::NT;
     constexpr int LDM = big_ldm(AT), ROWS = NV * AT, MTS = (ROWS + 7) / 8, XSTR = 8 * NT;
     constexpr int SH = (AT + 1) / 2;     // surfaces per lane in the O-factor stage
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -144,7 +198,6 @@ pbx_big_kernel(const BigParams Q) {
     // ---- model tables -> shared memory (once per CTA)
     double* tabs = sm;
     for (int i = threadIdx.x; i < Q.tab_doubles; i += blockDim.x) tabs[i] = Q.tab[i];
-    __syncthreads();
     const double* al = tabs + Q.o_al;        // [4][N]
     const double* ga = tabs + Q.o_ga;        // [4][N]
     const double* d2v = tabs + Q.o_d2v;      // [AT][N]
@@ -152,9 +205,41 @@ pbx_big_kernel(const BigParams Q) {
     const double* lpref = tabs + Q.o_lpref;  // [3][AT]
     const double* lprho = tabs + Q.o_lprho;  // [Ar]
     const double* drho = tabs + Q.o_drho;    // [Ar][N]
+    // feature table of the coupling contraction as byte offsets into a row of the coordinate tile
+    int* feat_s = reinterpret_cast<int*>(sm + big_even(Q.tab_doubles));      // [4 KS]
+    for (int i = threadIdx.x; i < 4 * Q.KS; i += blockDim.x) {
+        const int f = __ldg(Q.feat + i);
+        feat_s[i] = ((f & 0xffff) * BIG_RS * 8) | (((f >> 16) * BIG_RS * 8) << 16);
+    }
 
+    // ---- coefficient ring: BIG_STAGES stages of BIG_CH k-steps in fragment order + a full/empty mbarrier pair per stage
+    const int stage_doubles = BIG_CH * NT * 32;
+    double* ring = sm + big_even(Q.tab_doubles) + big_even(2 * Q.KS);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + (size_t)BIG_STAGES * stage_doubles);
+    uint64_t* bar_empty = bar_full + BIG_STAGES;
+    const long long nwarps = (long long)gridDim.x * BIG_WARPS;
+    const long long iters = (Q.n_samples - blockIdx.x + (long long)gridDim.x * BIG_WARPS - 1) / ((long long)gridDim.x * BIG_WARPS);
+    const int n_chunks = (Q.KS + BIG_CH - 1) / BIG_CH;
+    const long long total_chunks = iters * ((Q.P + BIG_G - 1) / BIG_G) * n_chunks;
+    const double* q_src = Q.q_dmma + (size_t)(blockIdx.x % BIG_TABLE_COPIES) * Q.q_copy_stride;
+    auto issue_chunk = [&](long long t, int slot) {      // chunk t of the CTA's sequence -> ring slot (one thread)
+        const int i = (int)(t % n_chunks), k0 = i * BIG_CH, nk = min(BIG_CH, Q.KS - k0);
+        const uint32_t bytes = (uint32_t)(nk * NT * 32 * sizeof(double));
+        big_mbar_expect_tx(&bar_full[slot], bytes);
+        big_bulk_copy(ring + (size_t)slot * stage_doubles, q_src + (size_t)k0 * NT * 32, bytes, &bar_full[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < BIG_STAGES; ++st) { big_mbar_init(&bar_full[st], 1); big_mbar_init(&bar_empty[st], BIG_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int st = 0; st < BIG_STAGES; ++st)
+            if (st < total_chunks) issue_chunk(st, st);
+    long long chunk_t = 0;        // chunks consumed so far: the same number in every warp of the CTA
     const BigLayout L = big_layout(AT, NV, N, Ar);
-    double* w = sm + big_even(Q.tab_doubles) + (size_t)warp * L.total;
+    double* w = sm + big_cta_doubles(Q.tab_doubles, Q.KS, NT) + (size_t)warp * L.total;
     double* Rt = w + L.regA;                 // [N+1][RS]; row N = ones
     double* bufs = w + L.regA;               // 3 x [AT][LDM]   (per-bead stage; Rt is dead then)
     double* Zt = w + L.regB;                 // [N][17] standard normals of the group (sampler)
@@ -201,10 +286,40 @@ pbx_big_kernel(const BigParams Q) {
 
     const uint2 key = make_uint2((uint32_t)Q.seed, (uint32_t)(Q.seed >> 32));
     const int H = (N + 1) / 2;
-    const long long nwarps = (long long)gridDim.x * BIG_WARPS;
+
+    // ---- ping-pong of the two warps that share a scheduler (warps w and w + BIG_WARPS/2): a group is a "V phase"
+    // (sampler, O factors, tensor-core V build: dense DMMA stream) followed by an "E phase" (per-bead exponential and chain:
+    // dependent products with shared-memory round trips).  Left alone the warps of a CTA run in step, both of a pair in
+    // the same phase, and the FP64 pipe idles whenever both sit in a bubble (ncu: DMMA 55 % + FP64 11 % active).  A named
+    // barrier per pair at every phase boundary, with the second warp one phase behind, keeps one warp's DMMA stream under
+    // the other's bubbles.  Both warps make the same number of barrier calls (the one with less work pads at the end).
+#if PBX_BIG_PINGPONG
+    constexpr int HALF = BIG_WARPS / 2;
+#if PBX_BIG_PAIRING == 0
+    const int pair_id = 1 + warp % HALF, role = warp / HALF, mate = role ? warp - HALF : warp + HALF;
+#else
+    const int pair_id = 1 + warp / 2, role = warp & 1, mate = warp ^ 1;
+#endif
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_id) : "memory"); };
+    long long sync_own = 0, sync_other = 0;
+    {
+        const int groups = (P + BIG_G - 1) / BIG_G;
+        (void)mate;
+        sync_own = 2 * iters * groups + role;        // two barriers per group: before and after the V build
+        sync_other = 2 * iters * groups + (1 - role);
+    }
+    if (role) pair_sync();
+#else
+    auto pair_sync = [&]() {};
+#endif
 
     // consecutive samples go to different SMs first, then to the next warp slot
-    for (long long x = (long long)warp * gridDim.x + blockIdx.x; x < Q.n_samples; x += nwarps) {
+    // every warp of the CTA makes the same number of passes (the ring protocol counts on it); a warp without a sample
+    // in the last pass recomputes the last sample and drops the result
+    for (long long it = 0; it < iters; ++it) {
+        long long x = (long long)warp * gridDim.x + blockIdx.x + it * nwarps;
+        const bool live = x < Q.n_samples;
+        if (!live) x = Q.n_samples - 1;
         const unsigned long long gidx = (unsigned long long)(Q.first_sample + x);
         // ---- sampler state (lane = mode): previous bead, first bead, shift of the drawn mixture component
         double yprev = 0.0, y0 = 0.0, shift = 0.0, rcarry = 0.0;
@@ -341,6 +456,7 @@ pbx_big_kernel(const BigParams Q) {
                 }
             }
 
+            pair_sync();       // E phase done: bead loop of the previous group, sampler and O factors of this one
             // ================================================================ V for the 16 beads on the FP64 tensor cores
             double acc[2][NT][2];
 #pragma unroll
@@ -348,37 +464,55 @@ pbx_big_kernel(const BigParams Q) {
 #pragma unroll
                 for (int j = 0; j < NT; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
             {
-                const double* qb = Q.q_dmma + lane;
-                const double* Rr = Rt + g;
-                const int KS = Q.KS;
-                double bq[2][NT];
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) bq[u][j] = (u < KS) ? __ldg(qb + ((size_t)u * NT + j) * 32) : 0.0;
-                int f = __ldg(Q.feat + c);
-                double a0 = Rr[(f & 0xffff) * BIG_RS] * Rr[(f >> 16) * BIG_RS];
-                double a1 = Rr[(f & 0xffff) * BIG_RS + 8] * Rr[(f >> 16) * BIG_RS + 8];
-                for (int ks = 0; ks < KS; ks += 2) {
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int k = ks + u;
-                        if (k < KS) {
-                            double n0 = 0.0, n1 = 0.0;
-                            if (k + 1 < KS) {       // A fragments of the next k-step
-                                f = __ldg(Q.feat + 4 * (k + 1) + c);
-                                n0 = Rr[(f & 0xffff) * BIG_RS] * Rr[(f >> 16) * BIG_RS];
-                                n1 = Rr[(f & 0xffff) * BIG_RS + 8] * Rr[(f >> 16) * BIG_RS + 8];
-                            }
-#pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                dmma_884(acc[0][j][0], acc[0][j][1], a0, bq[u][j]);
-                                dmma_884(acc[1][j][0], acc[1][j][1], a1, bq[u][j]);
-                                if (k + 2 < KS) bq[u][j] = __ldg(qb + ((size_t)(k + 2) * NT + j) * 32);
-                            }
-                            a0 = n0; a1 = n1;
+                // The coefficient fragments arrive through a shared-memory ring that one thread keeps filled with TMA bulk
+                // copies (cp.async.bulk + mbarrier): BIG_STAGES chunks of BIG_CH k-steps, read by all warps of the CTA --
+                // the table crosses L2 -> SM once per CTA and group instead of once per warp, and its latency is off the
+                // warps' critical path (with per-warp __ldg two k-steps ahead the first DMMA of every k-step waited ~150
+                // cycles on the long scoreboard; without the loads the kernel ran 15 % faster).
+                // A operands: three-stage software pipeline -- feature offsets of step k+3 and coordinate values of step
+                // k+2 are loaded before the tensor instructions of step k are issued, the products for step k+2 formed after.
+                const char* Rb = reinterpret_cast<const char*>(Rt + g);
+                const int KS = Q.KS, last = 4 * KS - 1;
+                auto rd = [&](int off) { return *reinterpret_cast<const double*>(Rb + off); };
+                int f = feat_s[c];
+                double a0 = rd(f & 0xffff) * rd(f >> 16), a1 = rd((f & 0xffff) + 64) * rd((f >> 16) + 64);
+                f = feat_s[min(4 + c, last)];
+                double b0 = rd(f & 0xffff) * rd(f >> 16), b1 = rd((f & 0xffff) + 64) * rd((f >> 16) + 64);
+                int fn = feat_s[min(8 + c, last)];
+                for (int i = 0; i < n_chunks; ++i, ++chunk_t) {
+                    const int slot = (int)(chunk_t % BIG_STAGES);
+                    if (threadIdx.x == 0 && chunk_t >= 1) {        // producer: the slot of chunk t-1 gets chunk t-1+STAGES
+                        const long long tn = chunk_t - 1 + BIG_STAGES;
+                        if (tn < total_chunks) {
+                            const int ps = (int)((chunk_t - 1) % BIG_STAGES);
+                            big_mbar_wait(&bar_empty[ps], (uint32_t)(((chunk_t - 1) / BIG_STAGES) & 1));
+                            issue_chunk(tn, ps);
                         }
                     }
+                    __syncwarp();
+                    big_mbar_wait(&bar_full[slot], (uint32_t)((chunk_t / BIG_STAGES) & 1));
+                    const double* bs = ring + (size_t)slot * stage_doubles + lane;
+#pragma unroll
+                    for (int u = 0; u < BIG_CH; ++u) {
+                        const int k = i * BIG_CH + u;
+                        if (k < KS) {
+                            const double ra0 = rd(fn & 0xffff), rb0 = rd(fn >> 16), ra1 = rd((fn & 0xffff) + 64), rb1 = rd((fn >> 16) + 64);
+                            fn = feat_s[min(4 * (k + 3) + c, last)];
+                            double bq[NT];
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) bq[j] = bs[(u * NT + j) * 32];
+                            __syncwarp();       // scheduling fence: the loads above stay in front of the tensor instructions
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                dmma_884(acc[0][j][0], acc[0][j][1], a0, bq[j]);
+                                dmma_884(acc[1][j][0], acc[1][j][1], a1, bq[j]);
+                            }
+                            a0 = b0; a1 = b1;
+                            b0 = ra0 * rb0; b1 = ra1 * rb1;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) big_mbar_arrive(&bar_empty[slot]);
                 }
             }
             __syncwarp();      // Tt / lrs (region B) are dead: the packed X tile takes their place
@@ -398,6 +532,7 @@ pbx_big_kernel(const BigParams Q) {
                 if (c == 0) nrm[8 * m + g] = fro;
             }
             __syncwarp();
+            pair_sync();       // V phase done
 
             // ================================================================ per bead: M = exp(X), chain step
             double* B0 = bufs;
@@ -485,11 +620,13 @@ pbx_big_kernel(const BigParams Q) {
 #pragma unroll
                     for (int mt = 0; mt < MTS; ++mt)
 #pragma unroll
-                        for (int nt = 0; nt < MT; ++nt) {
-                            cs[mt][nt][0] = 0.0; cs[mt][nt][1] = 0.0;
+                        for (int nt = 0; nt < MT; ++nt) { cs[mt][nt][0] = 0.0; cs[mt][nt][1] = 0.0; }
 #pragma unroll
-                            for (int ks = 0; ks < KSA; ++ks) dmma_884(cs[mt][nt][0], cs[mt][nt][1], as[mt][ks], oA.v[nt][ks]);
-                        }
+                    for (int ks = 0; ks < KSA; ++ks)
+#pragma unroll
+                        for (int mt = 0; mt < MTS; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < MT; ++nt) dmma_884(cs[mt][nt][0], cs[mt][nt][1], as[mt][ks], oA.v[nt][ks]);
                 }
                 __syncwarp();                                   // every lane has read its rows of T
                 const double* Op = ovib + jj * L.ov;
@@ -519,7 +656,7 @@ pbx_big_kernel(const BigParams Q) {
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             tr[v] = t;
         }
-        if (lane == 0) {
+        if (lane == 0 && live) {
             Q.out4[x] = rho;
 #pragma unroll
             for (int v = 0; v < NV; ++v) Q.out4[(size_t)(1 + v) * Q.out_ld + x] = tr[v];
@@ -531,11 +668,14 @@ pbx_big_kernel(const BigParams Q) {
         }
         __syncwarp();
     }
+#if PBX_BIG_PINGPONG
+    for (long long i = sync_own; i < sync_other; ++i) pair_sync();
+#endif
 }
 
 // shared memory of one CTA, bytes
-inline size_t big_smem_bytes(int A, bool pm, int N, int Ar, int tab_doubles) {
-    return ((size_t)big_even(tab_doubles) + (size_t)BIG_WARPS * big_layout(A, pm ? 3 : 1, N, Ar).total) * sizeof(double);
+inline size_t big_smem_bytes(int A, bool pm, int N, int Ar, int tab_doubles, int KS) {
+    return ((size_t)big_cta_doubles(tab_doubles, KS, (A * (A + 1) / 2 + 7) / 8) + (size_t)BIG_WARPS * big_layout(A, pm ? 3 : 1, N, Ar).total) * sizeof(double);
 }
 
 template <int AT>
