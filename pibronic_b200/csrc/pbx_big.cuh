@@ -145,15 +145,16 @@ __device__ __forceinline__ void big_prod(const BigOp<AT>& X, const BigOp<AT>& Y,
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < MT; ++nt) { C.v[mt][nt][0] = 0.0; C.v[mt][nt][1] = 0.0; }
+        for (int nt = 0; nt <= mt; ++nt) { C.v[mt][nt][0] = 0.0; C.v[mt][nt][1] = 0.0; }
     // k-step outermost: consecutive tensor instructions write different accumulator tiles (a dependent DMMA cannot
-    // issue until the previous one has left the pipe)
+    // issue until the previous one has left the pipe).  X and Y commute (polynomials of one matrix), the product is
+    // symmetric: only the tiles on and below the diagonal are formed (3 of 4 at A = 12), big_frag_store mirrors them.
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < MT; ++nt) dmma_884(C.v[mt][nt][0], C.v[mt][nt][1], X.v[mt][ks], Y.v[nt][ks]);
+            for (int nt = 0; nt <= mt; ++nt) dmma_884(C.v[mt][nt][0], C.v[mt][nt][1], X.v[mt][ks], Y.v[nt][ks]);
 }
 
 // operand fragment of a matrix in shared memory (row stride LDM): lane (g, c) holds M[8 t + g][4 ks + c]
@@ -169,17 +170,24 @@ __device__ __forceinline__ void big_op_load(const double* __restrict__ buf, BigO
         }
 }
 
-// accumulator fragment -> shared memory: lane (g, c) holds C[8 mt + g][8 nt + 2c + {0,1}]; one 16-byte store per tile
-// (a column AT of an odd-AT matrix lands in the row padding; its value is zero)
+// accumulator fragment of a SYMMETRIC matrix -> shared memory (full matrix): lane (g, c) holds C[8 mt + g][8 nt + 2c + {0,1}]
+// for the tiles nt <= mt; one 16-byte store per tile (a column AT of an odd-AT matrix lands in the row padding; its value
+// is zero) plus the transposed elements of the tiles below the diagonal
 template <int AT>
 __device__ __forceinline__ void big_frag_store(double* __restrict__ buf, const BigFrag<AT>& F, int g, int c) {
     constexpr int LDM = big_ldm(AT);
 #pragma unroll
     for (int mt = 0; mt < MidShape<AT>::MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < MidShape<AT>::MT; ++nt) {
+        for (int nt = 0; nt <= mt; ++nt) {
             const int i = 8 * mt + g, j = 8 * nt + 2 * c;
-            if (i < AT && j < AT) *reinterpret_cast<double2*>(buf + i * LDM + j) = make_double2(F.v[mt][nt][0], F.v[mt][nt][1]);
+            if (i < AT && j < AT) {
+                *reinterpret_cast<double2*>(buf + i * LDM + j) = make_double2(F.v[mt][nt][0], F.v[mt][nt][1]);
+                if (nt < mt) {      // the mirror image of an off-diagonal tile
+                    buf[j * LDM + i] = F.v[mt][nt][0];
+                    if (j + 1 < AT) buf[(j + 1) * LDM + i] = F.v[mt][nt][1];
+                }
+            }
         }
 }
 
@@ -490,22 +498,31 @@ pbx_big_kernel(const BigParams Q) {
                         }
                     }
                     __syncwarp();
+                    // coordinate values for the operands of step k+2 (first step of the chunk): issued before the wait
+                    double ra0 = rd(fn & 0xffff), rb0 = rd(fn >> 16), ra1 = rd((fn & 0xffff) + 64), rb1 = rd((fn >> 16) + 64);
+                    fn = feat_s[min(4 * (i * BIG_CH + 3) + c, last)];
                     big_mbar_wait(&bar_full[slot], (uint32_t)((chunk_t / BIG_STAGES) & 1));
                     const double* bs = ring + (size_t)slot * stage_doubles + lane;
+                    double bq[2][NT];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) bq[0][j] = bs[j * 32];
 #pragma unroll
                     for (int u = 0; u < BIG_CH; ++u) {
                         const int k = i * BIG_CH + u;
                         if (k < KS) {
-                            const double ra0 = rd(fn & 0xffff), rb0 = rd(fn >> 16), ra1 = rd((fn & 0xffff) + 64), rb1 = rd((fn >> 16) + 64);
-                            fn = feat_s[min(4 * (k + 3) + c, last)];
-                            double bq[NT];
+                            if (u > 0) {
+                                ra0 = rd(fn & 0xffff); rb0 = rd(fn >> 16); ra1 = rd((fn & 0xffff) + 64); rb1 = rd((fn >> 16) + 64);
+                                fn = feat_s[min(4 * (k + 3) + c, last)];
+                            }
+                            if (u + 1 < BIG_CH) {       // fragments of the next step of the chunk
 #pragma unroll
-                            for (int j = 0; j < NT; ++j) bq[j] = bs[(u * NT + j) * 32];
+                                for (int j = 0; j < NT; ++j) bq[(u + 1) & 1][j] = bs[((u + 1) * NT + j) * 32];
+                            }
                             __syncwarp();       // scheduling fence: the loads above stay in front of the tensor instructions
 #pragma unroll
                             for (int j = 0; j < NT; ++j) {
-                                dmma_884(acc[0][j][0], acc[0][j][1], a0, bq[j]);
-                                dmma_884(acc[1][j][0], acc[1][j][1], a1, bq[j]);
+                                dmma_884(acc[0][j][0], acc[0][j][1], a0, bq[u & 1][j]);
+                                dmma_884(acc[1][j][0], acc[1][j][1], a1, bq[u & 1][j]);
                             }
                             a0 = b0; a1 = b1;
                             b0 = ra0 * rb0; b1 = ra1 * rb1;
@@ -557,12 +574,12 @@ pbx_big_kernel(const BigParams Q) {
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < MT; ++nt)
+                    for (int nt = 0; nt <= mt; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) x1.v[mt][nt][e] = aci[mt][nt][e] >= 0 ? Xp[aci[mt][nt][e]] * scale : 0.0;
 #define PBX_FRAG_LOOP                                  \
     _Pragma("unroll") for (int mt = 0; mt < MT; ++mt)  \
-    _Pragma("unroll") for (int nt = 0; nt < MT; ++nt)  \
+    _Pragma("unroll") for (int nt = 0; nt <= mt; ++nt) \
     _Pragma("unroll") for (int e = 0; e < 2; ++e)
                 BigFrag<AT> x2, x3, y0f, fb, fo;
                 BigOp<AT> oA, oB;
