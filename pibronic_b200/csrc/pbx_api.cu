@@ -292,7 +292,8 @@ int upload_dmma_tables(pbx_plan* p) {
             for (int m = n; m < N; ++m) { fa.push_back(n); fb.push_back(m); coef.push_back(&H.q_pack[(size_t)pair_index(n, m, N) * AA]); }
     for (int n = 0; n < N; ++n) { fa.push_back(n); fb.push_back(ONE); coef.push_back(&H.l_off[(size_t)n * AA]); }
     fa.push_back(ONE); fb.push_back(ONE); coef.push_back(H.e_off.data());
-    const int K = (int)fa.size(), KS = (K + 3) / 4, NT = (AA + 7) / 8;
+    // k-steps of 4 features, padded (zero coefficients) to whole chunks of the fused kernel's coefficient ring
+    const int K = (int)fa.size(), KS = ((K + 3) / 4 + BIG_CH - 1) / BIG_CH * BIG_CH, NT = (AA + 7) / 8;
     std::vector<double> q((size_t)KS * NT * 32, 0.0);
     for (int ks = 0; ks < KS; ++ks)
         for (int j = 0; j < NT; ++j)

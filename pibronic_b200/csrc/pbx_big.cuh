@@ -23,29 +23,28 @@
 // Reference: /root/reference/pibronic/pimc/pimc.py:326-334, 613-631 (sampler), 1087-1129 (O), 1076-1084 (S),
 // 1132-1136 (rho), 1139-1187 (V, M), 1194-1209 (chain), 1413-1449 (order of operations in block_compute_pm).
 #pragma once
+#include <type_traits>
+
 #include "pbx_dmma.cuh"
 
 #ifndef PBX_BIG_WARPS
 #define PBX_BIG_WARPS 8
 #endif
-#ifndef PBX_BIG_PAIRING
-#define PBX_BIG_PAIRING 0      // which warps alternate: 0 = (w, w + BIG_WARPS/2), 1 = (2p, 2p + 1)
-#endif
 #ifndef PBX_BIG_CH
 #define PBX_BIG_CH 4           // k-steps per stage of the coefficient ring
 #endif
+#ifndef PBX_BIG_COPY_SPLIT
+#define PBX_BIG_COPY_SPLIT 1   // bulk copies per stage (must divide BIG_CH * NT * 2: every copy a multiple of 128 bytes)
+#endif
 #ifndef PBX_BIG_STAGES
 #define PBX_BIG_STAGES 3
-#endif
-#ifndef PBX_BIG_PINGPONG
-#define PBX_BIG_PINGPONG 0     // 1: the two warps of a scheduler alternate phases (named barriers), see the kernel
 #endif
 
 namespace pbx {
 
 constexpr int BIG_G = 16;            // beads per group: two m8 row tiles of the coupling contraction
 constexpr int BIG_RS = BIG_G + 2;    // row stride of the coordinate tile (17 beads: the group and the next one)
-constexpr int BIG_WARPS = PBX_BIG_WARPS, BIG_CH = PBX_BIG_CH, BIG_STAGES = PBX_BIG_STAGES;
+constexpr int BIG_WARPS = PBX_BIG_WARPS, BIG_CH = PBX_BIG_CH, BIG_STAGES = PBX_BIG_STAGES, BIG_COPY_SPLIT = PBX_BIG_COPY_SPLIT;
 #ifndef PBX_BIG_TABLE_COPIES
 #define PBX_BIG_TABLE_COPIES 16
 #endif
@@ -103,9 +102,10 @@ __host__ __device__ inline BigLayout big_layout(int A, int NV, int N, int Ar) {
     return L;
 }
 
-// doubles of CTA-shared tables in front of the per-warp regions: the constant table and the feature offsets [4 KS] (ints)
+// doubles of CTA-shared tables in front of the per-warp regions: the constant table, the feature offsets [4 KS] (int2),
+// the coefficient ring and its barriers
 __host__ __device__ inline int big_cta_doubles(int tab_doubles, int KS, int NT) {
-    return big_even(tab_doubles) + big_even(2 * KS) + BIG_STAGES * BIG_CH * NT * 32 + 2 * BIG_STAGES;
+    return big_even(tab_doubles) + 4 * KS + BIG_STAGES * BIG_CH * NT * 32 + 2 * BIG_STAGES;
 }
 
 // ---- mbarrier / TMA bulk-copy primitives (shared::cta)
@@ -214,27 +214,33 @@ pbx_big_kernel(const BigParams Q) {
     const double* lprho = tabs + Q.o_lprho;  // [Ar]
     const double* drho = tabs + Q.o_drho;    // [Ar][N]
     // feature table of the coupling contraction as byte offsets into a row of the coordinate tile
-    int* feat_s = reinterpret_cast<int*>(sm + big_even(Q.tab_doubles));      // [4 KS]
+    int2* feat_s = reinterpret_cast<int2*>(sm + big_even(Q.tab_doubles));     // [4 KS]
     for (int i = threadIdx.x; i < 4 * Q.KS; i += blockDim.x) {
         const int f = __ldg(Q.feat + i);
-        feat_s[i] = ((f & 0xffff) * BIG_RS * 8) | (((f >> 16) * BIG_RS * 8) << 16);
+        feat_s[i] = make_int2((f & 0xffff) * BIG_RS * 8, (f >> 16) * BIG_RS * 8);
     }
 
     // ---- coefficient ring: BIG_STAGES stages of BIG_CH k-steps in fragment order + a full/empty mbarrier pair per stage
     const int stage_doubles = BIG_CH * NT * 32;
-    double* ring = sm + big_even(Q.tab_doubles) + big_even(2 * Q.KS);
+    double* ring = sm + big_even(Q.tab_doubles) + 4 * Q.KS;
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + (size_t)BIG_STAGES * stage_doubles);
     uint64_t* bar_empty = bar_full + BIG_STAGES;
     const long long nwarps = (long long)gridDim.x * BIG_WARPS;
     const long long iters = (Q.n_samples - blockIdx.x + (long long)gridDim.x * BIG_WARPS - 1) / ((long long)gridDim.x * BIG_WARPS);
-    const int n_chunks = (Q.KS + BIG_CH - 1) / BIG_CH;
-    const long long total_chunks = iters * ((Q.P + BIG_G - 1) / BIG_G) * n_chunks;
+    const int n_chunks = Q.KS / BIG_CH;
+    // the CTA consumes the ring in one sequence of chunks, the same in every warp; slot and phase advance incrementally
+    // (no divisions on the critical path: thread 0, the producer, must not fall behind the other warps)
+    int chunks_left = (int)(iters * ((Q.P + BIG_G - 1) / BIG_G) * n_chunks);      // chunks this CTA has not consumed yet
     const double* q_src = Q.q_dmma + (size_t)(blockIdx.x % BIG_TABLE_COPIES) * Q.q_copy_stride;
-    auto issue_chunk = [&](long long t, int slot) {      // chunk t of the CTA's sequence -> ring slot (one thread)
-        const int i = (int)(t % n_chunks), k0 = i * BIG_CH, nk = min(BIG_CH, Q.KS - k0);
-        const uint32_t bytes = (uint32_t)(nk * NT * 32 * sizeof(double));
+    auto issue_chunk = [&](int i, int slot) {      // chunk i of the table -> ring slot (one thread)
+        const int k0 = i * BIG_CH;                          // KS is a multiple of BIG_CH (zero padded)
+        const uint32_t bytes = (uint32_t)(BIG_CH * NT * 32 * sizeof(double));
         big_mbar_expect_tx(&bar_full[slot], bytes);
-        big_bulk_copy(ring + (size_t)slot * stage_doubles, q_src + (size_t)k0 * NT * 32, bytes, &bar_full[slot]);
+        // BIG_COPY_SPLIT copies per stage (1 is best: a 10 KB copy lands in ~540 cycles, tools/microbench/bulk_copy_latency.cu)
+#pragma unroll
+        for (int q = 0; q < BIG_COPY_SPLIT; ++q)
+            big_bulk_copy(ring + (size_t)slot * stage_doubles + q * (stage_doubles / BIG_COPY_SPLIT),
+                          q_src + (size_t)k0 * NT * 32 + q * (stage_doubles / BIG_COPY_SPLIT), bytes / BIG_COPY_SPLIT, &bar_full[slot]);
     };
     if (threadIdx.x == 0) {
         for (int st = 0; st < BIG_STAGES; ++st) { big_mbar_init(&bar_full[st], 1); big_mbar_init(&bar_empty[st], BIG_WARPS); }
@@ -244,8 +250,10 @@ pbx_big_kernel(const BigParams Q) {
     __syncthreads();
     if (threadIdx.x == 0)
         for (int st = 0; st < BIG_STAGES; ++st)
-            if (st < total_chunks) issue_chunk(st, st);
-    long long chunk_t = 0;        // chunks consumed so far: the same number in every warp of the CTA
+            if (st < chunks_left) issue_chunk(st % n_chunks, st);
+    int r_slot = 0;               // ring slot and phase parity of the next chunk to consume
+    uint32_t r_phase = 0;
+    bool r_first = true;          // nothing consumed yet: no slot to refill
     const BigLayout L = big_layout(AT, NV, N, Ar);
     double* w = sm + big_cta_doubles(Q.tab_doubles, Q.KS, NT) + (size_t)warp * L.total;
     double* Rt = w + L.regA;                 // [N+1][RS]; row N = ones
@@ -294,32 +302,6 @@ pbx_big_kernel(const BigParams Q) {
 
     const uint2 key = make_uint2((uint32_t)Q.seed, (uint32_t)(Q.seed >> 32));
     const int H = (N + 1) / 2;
-
-    // ---- ping-pong of the two warps that share a scheduler (warps w and w + BIG_WARPS/2): a group is a "V phase"
-    // (sampler, O factors, tensor-core V build: dense DMMA stream) followed by an "E phase" (per-bead exponential and chain:
-    // dependent products with shared-memory round trips).  Left alone the warps of a CTA run in step, both of a pair in
-    // the same phase, and the FP64 pipe idles whenever both sit in a bubble (ncu: DMMA 55 % + FP64 11 % active).  A named
-    // barrier per pair at every phase boundary, with the second warp one phase behind, keeps one warp's DMMA stream under
-    // the other's bubbles.  Both warps make the same number of barrier calls (the one with less work pads at the end).
-#if PBX_BIG_PINGPONG
-    constexpr int HALF = BIG_WARPS / 2;
-#if PBX_BIG_PAIRING == 0
-    const int pair_id = 1 + warp % HALF, role = warp / HALF, mate = role ? warp - HALF : warp + HALF;
-#else
-    const int pair_id = 1 + warp / 2, role = warp & 1, mate = warp ^ 1;
-#endif
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_id) : "memory"); };
-    long long sync_own = 0, sync_other = 0;
-    {
-        const int groups = (P + BIG_G - 1) / BIG_G;
-        (void)mate;
-        sync_own = 2 * iters * groups + role;        // two barriers per group: before and after the V build
-        sync_other = 2 * iters * groups + (1 - role);
-    }
-    if (role) pair_sync();
-#else
-    auto pair_sync = [&]() {};
-#endif
 
     // consecutive samples go to different SMs first, then to the next warp slot
     // every warp of the CTA makes the same number of passes (the ring protocol counts on it); a warp without a sample
@@ -464,7 +446,6 @@ pbx_big_kernel(const BigParams Q) {
                 }
             }
 
-            pair_sync();       // E phase done: bead loop of the previous group, sampler and O factors of this one
             // ================================================================ V for the 16 beads on the FP64 tensor cores
             double acc[2][NT][2];
 #pragma unroll
@@ -479,57 +460,65 @@ pbx_big_kernel(const BigParams Q) {
                 // cycles on the long scoreboard; without the loads the kernel ran 15 % faster).
                 // A operands: three-stage software pipeline -- feature offsets of step k+3 and coordinate values of step
                 // k+2 are loaded before the tensor instructions of step k are issued, the products for step k+2 formed after.
+                // Per k-step a warp issues 20 tensor instructions (16 cycles of the FP64 pipe each) and ~20 others: the B
+                // fragments are refilled IN PLACE right after their last use (the register dependence keeps each shared-memory
+                // load between two tensor instructions, where the issue slot is free anyway), the A operands run two steps
+                // ahead.  A chunk (BIG_CH steps) is fully unrolled, without bounds checks: KS is padded to whole chunks.
                 const char* Rb = reinterpret_cast<const char*>(Rt + g);
-                const int KS = Q.KS, last = 4 * KS - 1;
+                const int last = 4 * Q.KS - 1;
                 auto rd = [&](int off) { return *reinterpret_cast<const double*>(Rb + off); };
-                int f = feat_s[c];
-                double a0 = rd(f & 0xffff) * rd(f >> 16), a1 = rd((f & 0xffff) + 64) * rd((f >> 16) + 64);
-                f = feat_s[min(4 + c, last)];
-                double b0 = rd(f & 0xffff) * rd(f >> 16), b1 = rd((f & 0xffff) + 64) * rd((f >> 16) + 64);
-                int fn = feat_s[min(8 + c, last)];
-                for (int i = 0; i < n_chunks; ++i, ++chunk_t) {
-                    const int slot = (int)(chunk_t % BIG_STAGES);
-                    if (threadIdx.x == 0 && chunk_t >= 1) {        // producer: the slot of chunk t-1 gets chunk t-1+STAGES
-                        const long long tn = chunk_t - 1 + BIG_STAGES;
-                        if (tn < total_chunks) {
-                            const int ps = (int)((chunk_t - 1) % BIG_STAGES);
-                            big_mbar_wait(&bar_empty[ps], (uint32_t)(((chunk_t - 1) / BIG_STAGES) & 1));
-                            issue_chunk(tn, ps);
-                        }
-                    }
-                    __syncwarp();
-                    // coordinate values for the operands of step k+2 (first step of the chunk): issued before the wait
-                    double ra0 = rd(fn & 0xffff), rb0 = rd(fn >> 16), ra1 = rd((fn & 0xffff) + 64), rb1 = rd((fn >> 16) + 64);
-                    fn = feat_s[min(4 * (i * BIG_CH + 3) + c, last)];
-                    big_mbar_wait(&bar_full[slot], (uint32_t)((chunk_t / BIG_STAGES) & 1));
-                    const double* bs = ring + (size_t)slot * stage_doubles + lane;
-                    double bq[2][NT];
+                int2 f = feat_s[c];
+                double a0 = rd(f.x) * rd(f.y), a1 = rd(f.x + 64) * rd(f.y + 64);      // step 0
+                f = feat_s[4 + c];
+                double b0 = rd(f.x) * rd(f.y), b1 = rd(f.x + 64) * rd(f.y + 64);      // step 1
+                int2 fn = feat_s[min(8 + c, last)];                                    // offsets of step 2
+                big_mbar_wait(&bar_full[r_slot], r_phase);
+                const double* bs = ring + (size_t)r_slot * stage_doubles + lane;
+                double bq[NT];
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) bq[0][j] = bs[j * 32];
+                for (int j = 0; j < NT; ++j) bq[j] = bs[j * 32];
+                for (int i = 0; i < n_chunks; ++i) {
+                    const int slot = r_slot;
+                    const int n_slot = (r_slot + 1 == BIG_STAGES) ? 0 : r_slot + 1;       // where the next chunk lives
+                    const uint32_t n_phase = r_phase ^ (n_slot == 0 ? 1u : 0u);
+                    if (threadIdx.x == 0 && !r_first && chunks_left >= BIG_STAGES) {
+                        // producer: the slot of the previous chunk gets the chunk BIG_STAGES - 1 ahead of this one
+                        const int ps = (r_slot == 0) ? BIG_STAGES - 1 : r_slot - 1;
+                        const uint32_t pp = r_phase ^ (r_slot == 0 ? 1u : 0u);
+                        int ti = i + BIG_STAGES - 1;
+                        while (ti >= n_chunks) ti -= n_chunks;
+                        big_mbar_wait(&bar_empty[ps], pp);
+                        issue_chunk(ti, ps);
+                    }
+                    r_first = false;
+                    __syncwarp();
+                    const double* bnext = bs;          // fragments of the first step of the next chunk
 #pragma unroll
                     for (int u = 0; u < BIG_CH; ++u) {
                         const int k = i * BIG_CH + u;
-                        if (k < KS) {
-                            if (u > 0) {
-                                ra0 = rd(fn & 0xffff); rb0 = rd(fn >> 16); ra1 = rd((fn & 0xffff) + 64); rb1 = rd((fn >> 16) + 64);
-                                fn = feat_s[min(4 * (k + 3) + c, last)];
-                            }
-                            if (u + 1 < BIG_CH) {       // fragments of the next step of the chunk
-#pragma unroll
-                                for (int j = 0; j < NT; ++j) bq[(u + 1) & 1][j] = bs[((u + 1) * NT + j) * 32];
-                            }
-                            __syncwarp();       // scheduling fence: the loads above stay in front of the tensor instructions
-#pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                dmma_884(acc[0][j][0], acc[0][j][1], a0, bq[u & 1][j]);
-                                dmma_884(acc[1][j][0], acc[1][j][1], a1, bq[u & 1][j]);
-                            }
-                            a0 = b0; a1 = b1;
-                            b0 = ra0 * rb0; b1 = ra1 * rb1;
+                        // coordinate values of step k+2, feature offsets of step k+3
+                        const double ra0 = rd(fn.x), rb0 = rd(fn.y), ra1 = rd(fn.x + 64), rb1 = rd(fn.y + 64);
+                        fn = feat_s[min(4 * (k + 3) + c, last)];
+                        const double* src = bs + (u + 1) * NT * 32;
+                        if (u == BIG_CH - 1) {          // the refills of the last step read the next chunk: wait for it here
+                            const bool more = i + 1 < n_chunks;
+                            if (more) big_mbar_wait(&bar_full[n_slot], n_phase);
+                            bnext = ring + (size_t)(more ? n_slot : slot) * stage_doubles + lane;
+                            src = bnext;
                         }
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            dmma_884(acc[0][j][0], acc[0][j][1], a0, bq[j]);
+                            dmma_884(acc[1][j][0], acc[1][j][1], a1, bq[j]);
+                            bq[j] = src[j * 32];
+                        }
+                        a0 = b0; a1 = b1;
+                        b0 = ra0 * rb0; b1 = ra1 * rb1;
                     }
                     __syncwarp();
                     if (lane == 0) big_mbar_arrive(&bar_empty[slot]);
+                    bs = bnext;
+                    r_slot = n_slot; r_phase = n_phase; --chunks_left;
                 }
             }
             __syncwarp();      // Tt / lrs (region B) are dead: the packed X tile takes their place
@@ -549,116 +538,143 @@ pbx_big_kernel(const BigParams Q) {
                 if (c == 0) nrm[8 * m + g] = fro;
             }
             __syncwarp();
-            pair_sync();       // V phase done
 
             // ================================================================ per bead: M = exp(X), chain step
+            // Software pipeline over the beads of the group: while the chain consumes M(jc) -- a (3A x A)(A x A) product
+            // of 10 independent accumulator tiles per k-step -- the exponential of the NEXT bead is formed; its four
+            // dependent products and their shared-memory round trips hide behind the chain's tensor instructions (done one
+            // after the other the two left the FP64 pipe idle half of the time).  step<chain, expm>(jc, je): the straight-
+            // line segments between two warp barriers hold a piece of each.
             double* B0 = bufs;
             double* B1 = bufs + AT * LDM;
             double* B2 = bufs + 2 * AT * LDM;
-            for (int jj = 0; jj < nb; ++jj) {
-                const double* Xp = Xs + jj * XSTR;
-                // squarings: smallest s >= 0 with ||X||_F / 2^s < theta  <=>  theta^-2 ||X||_F^2 < 4^s
-                int s = 0;
-                {
-                    const double y = nrm[jj] * (double)(PBX_EXPM_THETA_INV * PBX_EXPM_THETA_INV);
-                    if (y >= 1.0) s = ((((__double2hiint(y) >> 20) & 0x7ff) - 1023) >> 1) + 1;
-                    s = s > 60 ? 60 : s;
-                }
-                const double scale = __hiloint2double((1023 - s) << 20, 0);
-                BigOp<AT> oX;
-                BigFrag<AT> x1;
-#pragma unroll
-                for (int t = 0; t < MT; ++t)
-#pragma unroll
-                    for (int ks = 0; ks < KSA; ++ks) oX.v[t][ks] = opi[t][ks] >= 0 ? Xp[opi[t][ks]] * scale : 0.0;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt <= mt; ++nt)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) x1.v[mt][nt][e] = aci[mt][nt][e] >= 0 ? Xp[aci[mt][nt][e]] * scale : 0.0;
+            BigOp<AT> oM;                                       // M(jc) in operand layout
 #define PBX_FRAG_LOOP                                  \
     _Pragma("unroll") for (int mt = 0; mt < MT; ++mt)  \
     _Pragma("unroll") for (int nt = 0; nt <= mt; ++nt) \
     _Pragma("unroll") for (int e = 0; e < 2; ++e)
-                BigFrag<AT> x2, x3, y0f, fb, fo;
-                BigOp<AT> oA, oB;
-                big_prod<AT>(oX, oX, x2);                       // X^2
-                big_frag_store<AT>(B0, x2, g, c);
-                __syncwarp();
-                big_op_load<AT>(B0, oA, g, c);
-                big_prod<AT>(oX, oA, x3);                       // X^3
-                PBX_FRAG_LOOP fb.v[mt][nt][e] = fma(t12::c1, x3.v[mt][nt][e], fma(t12::c2, x2.v[mt][nt][e], t12::c3 * x1.v[mt][nt][e]));
-                big_frag_store<AT>(B1, x3, g, c);
-                big_frag_store<AT>(B2, fb, g, c);
-                __syncwarp();
-                big_op_load<AT>(B1, oA, g, c);
-                big_op_load<AT>(B2, oB, g, c);
-                big_prod<AT>(oA, oB, y0f);                      // Y0 = X^3 (c1 X^3 + c2 X^2 + c3 X)
-                PBX_FRAG_LOOP {
-                    fb.v[mt][nt][e] = y0f.v[mt][nt][e] + fma(t12::c4, x3.v[mt][nt][e], fma(t12::c5, x2.v[mt][nt][e], t12::c6 * x1.v[mt][nt][e]));
-                    fo.v[mt][nt][e] = y0f.v[mt][nt][e] + fma(t12::c7, x3.v[mt][nt][e], t12::c8 * x2.v[mt][nt][e]);
-                }
-                __syncwarp();                                   // every lane has read B1, B2
-                big_frag_store<AT>(B0, fb, g, c);
-                big_frag_store<AT>(B1, fo, g, c);
-                __syncwarp();
-                big_op_load<AT>(B0, oA, g, c);
-                big_op_load<AT>(B1, oB, g, c);
-                big_prod<AT>(oA, oB, fo);
-                PBX_FRAG_LOOP fo.v[mt][nt][e] = fo.v[mt][nt][e] +
-                    fma(t12::c9, y0f.v[mt][nt][e], fma(t12::c10, x3.v[mt][nt][e], fma(0.5, x2.v[mt][nt][e], x1.v[mt][nt][e]))) +
-                    (((8 * mt + g) == (8 * nt + 2 * c + e)) ? 1.0 : 0.0);
-#undef PBX_FRAG_LOOP
-                double* cur = B2;
-                double* nxt = B0;
-                big_frag_store<AT>(cur, fo, g, c);
-                __syncwarp();
-                big_op_load<AT>(cur, oA, g, c);                 // M (or its 2^s-th root) in operand layout
-                for (int q = 0; q < s; ++q) {
-                    big_prod<AT>(oA, oA, fo);
-                    big_frag_store<AT>(nxt, fo, g, c);
-                    __syncwarp();
-                    big_op_load<AT>(nxt, oA, g, c);
-                    double* t = cur; cur = nxt; nxt = t;          // the old buffer was last read before the barrier above
-                }
-
-                // ---- chain: [T_0; T_1; T_2] <- ([T_0; T_1; T_2] M) diag(O_v)      (pimc.py:1198-1206)
+            auto step = [&](auto chain_tag, auto expm_tag, const int jc, const int je) {
+                constexpr bool CHN = decltype(chain_tag)::value, EXP = decltype(expm_tag)::value;
+                BigOp<AT> oX, oA, oB;
+                BigFrag<AT> x1, x2, x3, y0f, fb, fo;
                 double cs[MTS][MT][2];
-                {
-                    double as[MTS][KSA];
-#pragma unroll
-                    for (int mt = 0; mt < MTS; ++mt)
-#pragma unroll
-                        for (int ks = 0; ks < KSA; ++ks) {
-                            const int r = 8 * mt + g, k = 4 * ks + c;
-                            as[mt][ks] = (r < ROWS && k < AT) ? Sst[r * LDM + k] : 0.0;
-                        }
+                int s = 0;
+                if constexpr (CHN) {
 #pragma unroll
                     for (int mt = 0; mt < MTS; ++mt)
 #pragma unroll
                         for (int nt = 0; nt < MT; ++nt) { cs[mt][nt][0] = 0.0; cs[mt][nt][1] = 0.0; }
+                }
+                // k-steps [lo, hi) of [T_0; T_1; T_2] M      (pimc.py:1198-1206)
+                auto chain_k = [&](const int lo, const int hi) {
 #pragma unroll
                     for (int ks = 0; ks < KSA; ++ks)
+                        if (ks >= lo && ks < hi) {
+                            double as[MTS];
 #pragma unroll
-                        for (int mt = 0; mt < MTS; ++mt)
+                            for (int mt = 0; mt < MTS; ++mt) {
+                                const int r = 8 * mt + g, k = 4 * ks + c;
+                                as[mt] = (r < ROWS && k < AT) ? Sst[r * LDM + k] : 0.0;
+                            }
 #pragma unroll
-                            for (int nt = 0; nt < MT; ++nt) dmma_884(cs[mt][nt][0], cs[mt][nt][1], as[mt][ks], oA.v[nt][ks]);
-                }
-                __syncwarp();                                   // every lane has read its rows of T
-                const double* Op = ovib + jj * L.ov;
+                            for (int mt = 0; mt < MTS; ++mt)
 #pragma unroll
-                for (int mt = 0; mt < MTS; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < MT; ++nt) {
-                        const int r = 8 * mt + g, j = 8 * nt + 2 * c;
-                        if (r < ROWS && j < AT) {
-                            const double o0 = Op[vrow[mt] * AT + j], o1 = (j + 1 < AT) ? Op[vrow[mt] * AT + j + 1] : 0.0;
-                            *reinterpret_cast<double2*>(Sst + r * LDM + j) = make_double2(cs[mt][nt][0] * o0, cs[mt][nt][1] * o1);
+                                for (int nt = 0; nt < MT; ++nt) dmma_884(cs[mt][nt][0], cs[mt][nt][1], as[mt], oM.v[nt][ks]);
                         }
-                    }
+                };
+                // ---- segment 0: X^2
+                if constexpr (EXP) {
+                    const double* Xp = Xs + je * XSTR;
+                    // squarings: smallest s >= 0 with ||X||_F / 2^s < theta  <=>  theta^-2 ||X||_F^2 < 4^s
+                    const double y = nrm[je] * (double)(PBX_EXPM_THETA_INV * PBX_EXPM_THETA_INV);
+                    if (y >= 1.0) s = ((((__double2hiint(y) >> 20) & 0x7ff) - 1023) >> 1) + 1;
+                    s = s > 60 ? 60 : s;
+                    const double scale = __hiloint2double((1023 - s) << 20, 0);
+#pragma unroll
+                    for (int t = 0; t < MT; ++t)
+#pragma unroll
+                        for (int ks = 0; ks < KSA; ++ks) oX.v[t][ks] = opi[t][ks] >= 0 ? Xp[opi[t][ks]] * scale : 0.0;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt <= mt; ++nt)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) x1.v[mt][nt][e] = aci[mt][nt][e] >= 0 ? Xp[aci[mt][nt][e]] * scale : 0.0;
+                }
+                if constexpr (CHN) chain_k(0, 1);
+                if constexpr (EXP) {
+                    big_prod<AT>(oX, oX, x2);                       // X^2
+                    big_frag_store<AT>(B0, x2, g, c);
+                }
                 __syncwarp();
-            }
+                // ---- segment 1: X^3 and the first factor of Y0
+                if constexpr (CHN) chain_k(1, 2);
+                if constexpr (EXP) {
+                    big_op_load<AT>(B0, oA, g, c);
+                    big_prod<AT>(oX, oA, x3);                       // X^3
+                    PBX_FRAG_LOOP fb.v[mt][nt][e] = fma(t12::c1, x3.v[mt][nt][e], fma(t12::c2, x2.v[mt][nt][e], t12::c3 * x1.v[mt][nt][e]));
+                    big_frag_store<AT>(B1, x3, g, c);
+                    big_frag_store<AT>(B2, fb, g, c);
+                }
+                __syncwarp();
+                // ---- segment 2: Y0 = X^3 (c1 X^3 + c2 X^2 + c3 X)
+                if constexpr (CHN) chain_k(2, KSA);
+                if constexpr (EXP) {
+                    big_op_load<AT>(B1, oA, g, c);
+                    big_op_load<AT>(B2, oB, g, c);
+                    big_prod<AT>(oA, oB, y0f);
+                    PBX_FRAG_LOOP {
+                        fb.v[mt][nt][e] = y0f.v[mt][nt][e] + fma(t12::c4, x3.v[mt][nt][e], fma(t12::c5, x2.v[mt][nt][e], t12::c6 * x1.v[mt][nt][e]));
+                        fo.v[mt][nt][e] = y0f.v[mt][nt][e] + fma(t12::c7, x3.v[mt][nt][e], t12::c8 * x2.v[mt][nt][e]);
+                    }
+                }
+                __syncwarp();                                   // every lane has read B1, B2 and its rows of T
+                // ---- segment 3: T <- (T M) diag(O_v); the two factors of the last product
+                if constexpr (CHN) {
+                    const double* Op = ovib + jc * L.ov;
+#pragma unroll
+                    for (int mt = 0; mt < MTS; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < MT; ++nt) {
+                            const int r = 8 * mt + g, j = 8 * nt + 2 * c;
+                            if (r < ROWS && j < AT) {
+                                const double o0 = Op[vrow[mt] * AT + j], o1 = (j + 1 < AT) ? Op[vrow[mt] * AT + j + 1] : 0.0;
+                                *reinterpret_cast<double2*>(Sst + r * LDM + j) = make_double2(cs[mt][nt][0] * o0, cs[mt][nt][1] * o1);
+                            }
+                        }
+                }
+                if constexpr (EXP) {
+                    big_frag_store<AT>(B0, fb, g, c);
+                    big_frag_store<AT>(B1, fo, g, c);
+                }
+                __syncwarp();
+                // ---- segment 4: T12 = (Y0 + c4 X^3 + c5 X^2 + c6 X)(Y0 + c7 X^3 + c8 X^2) + c9 Y0 + c10 X^3 + X^2/2 + X + I
+                if constexpr (EXP) {
+                    big_op_load<AT>(B0, oA, g, c);
+                    big_op_load<AT>(B1, oB, g, c);
+                    big_prod<AT>(oA, oB, fo);
+                    PBX_FRAG_LOOP fo.v[mt][nt][e] = fo.v[mt][nt][e] +
+                        fma(t12::c9, y0f.v[mt][nt][e], fma(t12::c10, x3.v[mt][nt][e], fma(0.5, x2.v[mt][nt][e], x1.v[mt][nt][e]))) +
+                        (((8 * mt + g) == (8 * nt + 2 * c + e)) ? 1.0 : 0.0);
+                    double* cur = B2;
+                    double* nxt = B0;
+                    big_frag_store<AT>(cur, fo, g, c);
+                    __syncwarp();
+                    big_op_load<AT>(cur, oM, g, c);                 // M (or its 2^s-th root) in operand layout
+                    for (int q = 0; q < s; ++q) {
+                        big_prod<AT>(oM, oM, fo);
+                        big_frag_store<AT>(nxt, fo, g, c);
+                        __syncwarp();
+                        big_op_load<AT>(nxt, oM, g, c);
+                        double* t = cur; cur = nxt; nxt = t;          // the old buffer was last read before the barrier above
+                    }
+                    __syncwarp();                               // B0..B2 are rewritten by the next step
+                }
+            };
+            step(std::false_type{}, std::true_type{}, 0, 0);                          // M(0)
+            for (int jj = 0; jj + 1 < nb; ++jj) step(std::true_type{}, std::true_type{}, jj, jj + 1);
+            step(std::true_type{}, std::false_type{}, nb - 1, 0);                     // last bead of the group
+#undef PBX_FRAG_LOOP
         }
 
         // ---- rho(x) = sum_a exp(sum_p log(O_rho[a]/S)); g_v(x) = tr T_v
@@ -685,9 +701,6 @@ pbx_big_kernel(const BigParams Q) {
         }
         __syncwarp();
     }
-#if PBX_BIG_PINGPONG
-    for (long long i = sync_own; i < sync_other; ++i) pair_sync();
-#endif
 }
 
 // shared memory of one CTA, bytes
