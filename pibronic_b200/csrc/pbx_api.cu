@@ -358,6 +358,7 @@ int upload_big_tables(pbx_plan* p) {
     B.tab = p->big_tab;
     B.Ar = Ar; B.N = N; B.P = H.P; B.n_rho_eval = H.n_rho_eval; B.KS = p->D.KS; B.neg_tau = -H.tau[0];
     B.q_copy_stride = (long long)p->D.KS * p->D.NT * 32;
+    B.share = H.rho_shares_vib ? 1 : 0;
     B.wcum = p->D.wcum; B.q_dmma = p->D.q_dmma; B.feat = p->D.feat; B.tri_ij = p->D.tri_ij; B.samp = p->D.samp;
     return PBX_OK;
 }

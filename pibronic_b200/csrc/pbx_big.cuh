@@ -55,6 +55,7 @@ enum { BIG_COORDS = 0, BIG_SAMPLE = 1 };
 
 struct BigParams {
     int Ar, N, P, n_rho_eval, KS;   // KS: k-steps (4 features each) of the coupling contraction
+    int share;                      // 1: rho has the model's diagonal shifts and frequencies (HostTables::rho_shares_vib)
     double neg_tau;
     // flat table staged into shared memory at kernel start: al[4][N], ga[4][N] (-1/4 tanh(x/2), -1/4 coth(x/2); rows vib
     // tau, tau+, tau-, rho), d2v[A][N], d2r[Ar][N] (2 d), lpref[3][A], lprho[Ar], drho[Ar][N]
@@ -348,13 +349,24 @@ pbx_big_kernel(const BigParams Q) {
                 if (lane < N) {
                     double* row = Rt + lane * BIG_RS;
                     if (p0 > 0) row[0] = rcarry;
-                    for (int j = jlo; j <= jhi; ++j) {
-                        const double* tb = Q.samp + ((size_t)j * N + lane) * 3;
-                        double y = __ldg(tb) * Zt[lane * (BIG_G + 1) + (j - p0)];
-                        if (j > 0) y = fma(__ldg(tb + 1), yprev, fma(__ldg(tb + 2), y0, y));
-                        if (j == 0) y0 = y;
-                        yprev = y;
-                        row[j - p0] = y + shift;
+                    for (int j4 = jlo; j4 <= jhi; j4 += 4) {        // recurrence coefficients of four beads at a time: one latency
+                        double ca[4], cb[4], ce[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double* tb = Q.samp + ((size_t)min(j4 + q, jhi) * N + lane) * 3;
+                            ca[q] = __ldg(tb); cb[q] = __ldg(tb + 1); ce[q] = __ldg(tb + 2);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = j4 + q;
+                            if (j <= jhi) {
+                                double y = ca[q] * Zt[lane * (BIG_G + 1) + (j - p0)];
+                                if (j > 0) y = fma(cb[q], yprev, fma(ce[q], y0, y));
+                                if (j == 0) y0 = y;
+                                yprev = y;
+                                row[j - p0] = y + shift;
+                            }
+                        }
                     }
                     if (p0 + BIG_G >= P) row[P - p0] = y0 + shift;            // the ring closes on bead 0
                     for (int col = min(BIG_G, P - p0) + 1; col <= BIG_G; ++col) row[col] = 0.0;
@@ -407,6 +419,18 @@ pbx_big_kernel(const BigParams Q) {
                     }
                 }
                 double lmax = -INFINITY;
+                if (Q.share) {
+                    // rho is the diagonal of the model (same shifts and frequencies): its exponent sums are those of the tau set
+#pragma unroll
+                    for (int s = 0; s < SH; ++s) {
+                        const int a = hf + 2 * s;
+                        if (a < AT) {
+                            const double lr = (a < Q.n_rho_eval) ? lprho[a] + (gsum[0] + ev[0][s]) : -INFINITY;
+                            lrs[jb * Ar + a] = lr;
+                            lmax = fmax(lmax, lr);
+                        }
+                    }
+                }
 #pragma unroll
                 for (int s = 0; s < SH; ++s) {
                     const int a = min(hf + 2 * s, AT - 1);
@@ -415,7 +439,7 @@ pbx_big_kernel(const BigParams Q) {
                     lmax = fmax(lmax, ev[0][s]);
                 }
                 // sampling surfaces a = hf, hf + 2, ... < Ar
-                for (int a = hf; a < Ar; a += 2) {
+                for (int a = hf; a < (Q.share ? 0 : Ar); a += 2) {
                     double acc = gsum[NV];
                     const double* d2 = d2r + a * N;
                     for (int n = 0; n < N; ++n) {
