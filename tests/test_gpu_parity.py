@@ -410,22 +410,69 @@ def test_full_size_c2_properties(cuda):
     plan.close()
 
 
-def test_c4_shape_runs_on_generic_kernels(cuda):
-    """A=12, N=24, P=256 (BASELINE.json configs[3]) at a handful of samples against the oracle"""
-    from oracle import pimc_oracle as orc
+def _c4_plan(extra=0, pm=True):
     from pibronic_b200 import constants, synthetic
     from pibronic_b200.model_io import VMK
     model = synthetic.model_c4()
     rho = synthetic.diagonal_of(model)
     plan = _cabi.Plan(model[VMK.E], model[VMK.w], model[VMK.G1], model[VMK.G2], rho[VMK.E], rho[VMK.w], rho[VMK.G1],
-                      256, constants.beta(300.0), constants.delta_beta, flags=_cabi.FLAG_PM, device=0)
-    assert not plan.is_fast
-    n = 6
-    out = plan.sample_eval_host(1, 0, n)
-    R, _ = drawn_coords(cuda, plan, 1, 0, n)
+                      256, constants.beta(300.0), constants.delta_beta, flags=(_cabi.FLAG_PM if pm else 0) | extra, device=0)
     vib_d = dict(A=12, N=24, E=model[VMK.E], w=model[VMK.w], L=model[VMK.G1], Q=model[VMK.G2])
     rho_d = dict(A=12, N=24, E=rho[VMK.E], w=rho[VMK.w], L=rho[VMK.G1])
+    return plan, vib_d, rho_d
+
+
+def test_c4_shape_runs_on_the_fused_tensor_core_kernel(cuda):
+    """A=12, N=24, P=256 (BASELINE.json configs[3]): one launch of the fused large-A kernel (sampler on chip, no scratch)
+    against the oracle on the coordinates the sampler kernel reports for the same Philox counters, and against the
+    blocked kernels of round 1; n = 19 leaves most warps of the CTAs without a sample"""
+    from oracle import pimc_oracle as orc
+    plan, vib_d, rho_d = _c4_plan()
+    assert not plan.is_fast and plan.kernel_path == _cabi.PATH_FUSED_DMMA
+    n = 19
+    launches = plan.launch_count
+    out = plan.sample_eval_host(1, 0, n)
+    assert plan.launch_count - launches == 1                      # sampler + estimator in ONE kernel
+    R, _ = drawn_coords(cuda, plan, 1, 0, n)
     tab = orc.precompute(vib_d, rho_d, 256, 300.0)
+    assert rel_err(out, oracle_eval(tab, R)) < RTOL
+    assert np.array_equal(out, plan.eval_coords_host(R))          # same arithmetic on caller supplied coordinates
+    blocked, _, _ = _c4_plan(_cabi.FLAG_NO_FUSED_DMMA)
+    assert blocked.kernel_path == _cabi.PATH_BLOCKED
+    assert rel_err(blocked.sample_eval_host(1, 0, n), out) < RTOL
+    blocked.close()
+    plan.close()
+
+
+def test_fused_tensor_core_kernel_many_passes_and_splits(cuda):
+    """more samples than resident warps (148 SMs x 8): several passes per warp, a partly filled last pass, results
+    independent of how the index range is cut, non-PM variant fills two rows"""
+    plan, _, _ = _c4_plan()
+    n, seed, first = 148 * 8 + 77, 5, (1 << 33) + 11
+    whole = plan.sample_eval_host(seed, first, n)
+    assert np.all(np.isfinite(whole)) and np.all(whole[0] > 0)
+    parts = np.concatenate([plan.sample_eval_host(seed, first, 300), plan.sample_eval_host(seed, first + 300, n - 300)], axis=1)
+    assert np.array_equal(whole, parts)
+    plan.close()
+    plain, _, _ = _c4_plan(pm=False)
+    two = plain.sample_eval_host(seed, first, 64, out4=np.full((2, 64), np.nan))
+    assert np.array_equal(two, whole[:2, :64])
+    plain.close()
+
+
+@pytest.mark.parametrize("P", [3, 16, 17, 33])
+def test_fused_tensor_core_kernel_bead_counts(cuda, P):
+    """bead counts around the 16-bead group size of the fused kernel (ring closure inside / at the edge of a group)"""
+    from conftest import GoldenCase
+    from oracle import pimc_oracle as orc
+    case = GoldenCase("syn_7x12")
+    flags = _cabi.FLAG_PM | _cabi.QUIRK_RHO_TRUNC
+    plan = _cabi.Plan(case.vib["E"], case.vib["w"], case.vib["L"], case.vib["Q"], case.rho["E"], case.rho["w"],
+                      case.rho["L"], P, orc.beta_of(case.T), orc.DELTA_BETA, flags=flags, device=0)
+    assert plan.kernel_path == _cabi.PATH_FUSED_DMMA
+    tab = orc.precompute(case.vib, case.rho, P, case.T, rho_trunc=True)
+    out = plan.sample_eval_host(9, 100, 40)
+    R, _ = drawn_coords(cuda, plan, 9, 100, 40)
     assert rel_err(out, oracle_eval(tab, R)) < RTOL
     plan.close()
 
