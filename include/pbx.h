@@ -70,7 +70,9 @@ enum {
                                        /* producer/consumer (warp-specialised) one; same results bit for bit  */
     PBX_FLAG_NO_FUSED_DMMA  = 1u << 7, /* 2 <= A <= 16 without a register-resident kernel: the blocked kernels   */
                                        /* through HBM scratch instead of the fused one-launch tensor-core kernel  */
-    PBX_FLAG_PREFER_DMMA    = 1u << 8  /* use the fused tensor-core kernel even where a register-resident one exists */
+    PBX_FLAG_PREFER_DMMA    = 1u << 8, /* use the fused tensor-core kernel even where a register-resident one exists */
+    PBX_QUIRK_RHO_DOUBLE_SHIFT = 1u << 9 /* reference quirk pimc.py:1293-1298 (block_compute_rhoR_from_input_samples): rho(R) is   */
+                                       /* evaluated at R - d_vib[a] - d_rho[a] instead of R - d_rho[a]; needs A_rho == A      */
 };
 
 /* which kernel family a plan runs on (pbx_plan_kernel_path) */

@@ -23,6 +23,7 @@ FLAG_NO_SCALING = 1 << 5
 FLAG_NO_WARPSPEC = 1 << 6
 FLAG_NO_FUSED_DMMA = 1 << 7
 FLAG_PREFER_DMMA = 1 << 8
+QUIRK_RHO_DOUBLE_SHIFT = 1 << 9
 PATH_GENERIC, PATH_REGISTER, PATH_BLOCKED, PATH_FUSED_DMMA = 0, 1, 2, 3
 NSUMS = 8
 SUM_NAMES = ("r", "r_plus", "r_minus", "r_sq", "d1", "d2", "d1_sq", "d2_sq")

@@ -266,7 +266,8 @@ int upload_tables(pbx_plan* p) {
     auto push = [&](const std::vector<double>& v) { size_t off = flat.size(); flat.insert(flat.end(), v.begin(), v.end()); return off; };
     std::vector<double> hc(H.coth.size()), cs(H.csch);
     for (size_t i = 0; i < hc.size(); ++i) hc[i] = -0.5 * H.coth[i];
-    const size_t o_dv = push(H.d_vib), o_dr = push(H.d_rho), o_hc = push(hc), o_cs = push(cs), o_lp = push(H.logpref),
+    const size_t o_drs = push(H.d_rho);
+    const size_t o_dv = push(H.d_vib), o_dr = push(H.d_rho_eval), o_hc = push(hc), o_cs = push(cs), o_lp = push(H.logpref),
                  o_lpr = push(H.logpref_rho), o_wc = push(H.wcum), o_e = push(H.e_off), o_l = push(H.l_off),
                  o_q = push(H.q_pack), o_s = push(H.samp);
     PBX_CUDA(cudaMalloc((void**)&p->dev_tables, flat.size() * sizeof(double)));
@@ -275,6 +276,7 @@ int upload_tables(pbx_plan* p) {
     D.A = H.A; D.Ar = H.Ar; D.N = H.N; D.P = H.P; D.AA = H.AA; D.NN = H.NN; D.n_rho_eval = H.n_rho_eval;
     D.neg_tau = -H.tau[0];
     const double* b = p->dev_tables;
+    D.d_rho_samp = b + o_drs;
     D.d_vib = b + o_dv; D.d_rho = b + o_dr; D.hc = b + o_hc; D.cs = b + o_cs; D.lpref = b + o_lp;
     D.lpref_rho = b + o_lpr; D.wcum = b + o_wc; D.e_off = b + o_e; D.l_off = b + o_l; D.q_pack = b + o_q;
     D.samp = b + o_s;
@@ -340,7 +342,7 @@ int upload_big_tables(pbx_plan* p) {
     B.o_d2v = (int)flat.size();
     for (int i = 0; i < A * N; ++i) flat.push_back(2.0 * H.d_vib[i]);
     B.o_d2r = (int)flat.size();
-    for (int i = 0; i < Ar * N; ++i) flat.push_back(2.0 * H.d_rho[i]);
+    for (int i = 0; i < Ar * N; ++i) flat.push_back(2.0 * H.d_rho_eval[i]);
     B.o_lpref = (int)flat.size();
     flat.insert(flat.end(), H.logpref.begin(), H.logpref.end());
     B.o_lprho = (int)flat.size();
@@ -580,7 +582,7 @@ int64_t pbx_plan_table(const pbx_plan* p, const char* name, double* out, int64_t
     const std::vector<double>* v = nullptr;
     std::vector<double> tmp;
     const std::string s(name);
-    if (s == "d_vib") v = &H.d_vib; else if (s == "d_rho") v = &H.d_rho;
+    if (s == "d_vib") v = &H.d_vib; else if (s == "d_rho") v = &H.d_rho; else if (s == "d_rho_eval") v = &H.d_rho_eval;
     else if (s == "delta_vib") v = &H.delta_vib; else if (s == "delta_rho") v = &H.delta_rho;
     else if (s == "weights") v = &H.weights; else if (s == "coth") v = &H.coth; else if (s == "csch") v = &H.csch;
     else if (s == "logpref") v = &H.logpref; else if (s == "logpref_rho") v = &H.logpref_rho;

@@ -460,7 +460,7 @@ void fill_fast_tables(const HostTables& H, void* dst) {
     auto& T = *reinterpret_cast<FastTables<A, N, AR>*>(dst);
     constexpr int AA = A * (A + 1) / 2, NN = N * (N + 1) / 2;
     for (int a = 0; a < A; ++a) for (int n = 0; n < N; ++n) T.d2_vib[a][n] = 2.0 * H.d_vib[a * N + n];
-    for (int a = 0; a < AR; ++a) for (int n = 0; n < N; ++n) { T.d_rho[a][n] = H.d_rho[a * N + n]; T.d2_rho[a][n] = 2.0 * H.d_rho[a * N + n]; }
+    for (int a = 0; a < AR; ++a) for (int n = 0; n < N; ++n) { T.d_rho[a][n] = H.d_rho[a * N + n]; T.d2_rho[a][n] = 2.0 * H.d_rho_eval[a * N + n]; }
     for (int v = 0; v < 4; ++v) for (int n = 0; n < N; ++n) { T.al[v][n] = -0.25 * H.tanh_half[v * N + n]; T.ga[v][n] = -0.25 * H.coth_half[v * N + n]; }
     for (int v = 0; v < 2; ++v) for (int n = 0; n < N; ++n) { T.dal[v][n] = -0.25 * H.dtanh_half[v * N + n]; T.dga[v][n] = -0.25 * H.dcoth_half[v * N + n]; }
     for (int v = 0; v < 3; ++v) for (int a = 0; a < A; ++a) T.lpref[v][a] = H.logpref[v * A + a];

@@ -17,7 +17,8 @@ namespace pbx {
 struct DevTables {
     int A, Ar, N, P, AA, NN, n_rho_eval;
     double neg_tau;
-    const double *d_vib, *d_rho;     // [A][N], [Ar][N]
+    const double *d_vib, *d_rho;     // [A][N], [Ar][N]: shifts in the harmonic exponents
+    const double *d_rho_samp;        // [Ar][N]: shift of the drawn mixture component (== d_rho unless PBX_QUIRK_RHO_DOUBLE_SHIFT)
     const double *hc, *cs;           // [4][N]  (-0.5 coth, csch)
     const double *lpref, *lpref_rho; // [3][A], [Ar]
     const double *wcum;              // [Ar]

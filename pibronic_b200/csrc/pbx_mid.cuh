@@ -57,7 +57,7 @@ pbx_mid_sample_kernel(DevTables T, unsigned long long seed, long long first_samp
     if (src_out && h == 0) src_out[x] = src;
     double y0[2] = {0.0, 0.0}, yprev[2] = {0.0, 0.0}, shift[2];
 #pragma unroll
-    for (int w = 0; w < 2; ++w) shift[w] = (2 * h + w < N) ? T.d_rho[src * N + 2 * h + w] : 0.0;
+    for (int w = 0; w < 2; ++w) shift[w] = (2 * h + w < N) ? T.d_rho_samp[src * N + 2 * h + w] : 0.0;
     double* Rx = R + (size_t)x * N * P;
     for (int j = 0; j < P; ++j) {
         const double* tab = T.samp + ((size_t)j * N + 2 * h) * 3;

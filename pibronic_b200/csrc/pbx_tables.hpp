@@ -31,6 +31,7 @@ struct HostTables {
     double beta = 0, delta_beta = 0;
     double tau[3] = {0, 0, 0};  // tau, tau+, tau-
     std::vector<double> d_vib, d_rho, delta_vib, delta_rho, weights, wcum;
+    std::vector<double> d_rho_eval;       // shift used in rho's harmonic exponent: d_rho (+ d_vib under PBX_QUIRK_RHO_DOUBLE_SHIFT)
     std::vector<double> coth, csch;       // [4][N]: vib tau, vib tau+, vib tau-, rho tau (rho's own omega)
     std::vector<double> logpref;          // [3][A]
     // differences of the tau+ / tau- tables from the tau ones, formed analytically (not by subtracting
@@ -149,6 +150,11 @@ inline int build_tables(const pbx_model* vib, const pbx_rho* rho, int P, double 
         tilde_r[a] = (long double)rho->energy[a] + (long double)T.delta_rho[a];
         if (a == 0 || tilde_r[a] < tmin) tmin = tilde_r[a];
     }
+    T.d_rho_eval = T.d_rho;
+    if (flags & PBX_QUIRK_RHO_DOUBLE_SHIFT) {
+        if (Ar != A) { err = "PBX_QUIRK_RHO_DOUBLE_SHIFT needs a sampling model with as many surfaces as the system"; return PBX_ERR_ARG; }
+        for (int i = 0; i < A * N; ++i) T.d_rho_eval[i] += T.d_vib[i];
+    }
     {   // weights ~ exp(-beta*tilde) (the common 1/prod sinh factor cancels in the normalisation)
         long double total = 0.0L;
         std::vector<long double> w(Ar);
@@ -221,7 +227,7 @@ inline int build_tables(const pbx_model* vib, const pbx_rho* rho, int P, double 
     for (int n = 0; n < N && T.rho_shares_vib; ++n) {
         if (vib->omega[n] != rho->omega[n]) T.rho_shares_vib = false;
         for (int a = 0; a < A && a < Ar; ++a)
-            if (T.d_vib[a * N + n] != T.d_rho[a * N + n]) T.rho_shares_vib = false;
+            if (T.d_vib[a * N + n] != T.d_rho_eval[a * N + n]) T.rho_shares_vib = false;
     }
     // ---- sampler recurrence, one (a,b,e) triple per (bead, mode); precision = 2coth - csch*C
     T.samp.assign((size_t)P * N * 3, 0.0);

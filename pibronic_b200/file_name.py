@@ -13,6 +13,21 @@ def jackknife(P="{P:d}", T="{T:.2f}", X="{X:d}"):
     return "P{:s}_T{:s}_X{:s}_thermo".format(P, T, X)
 
 
+def training_data_input(P="{P:d}", T="{T:.2f}", J="{J:d}"):
+    """bead co-ordinates of a g(R) / rho(R) run (training sets for ML models, file_name.py:98-106)"""
+    return "P{:s}_T{:s}_J{:s}_training_data_input.npz".format(P, T, J)
+
+
+def training_data_g_output(P="{P:d}", T="{T:.2f}", J="{J:d}"):
+    """g(R) of a training-set run (file_name.py:114-122)"""
+    return "P{:s}_T{:s}_J{:s}_training_data_g_output.npz".format(P, T, J)
+
+
+def training_data_rho_output(P="{P:d}", T="{T:.2f}", J="{J:d}"):
+    """rho(R) of a training-set run (file_name.py:130-138)"""
+    return "P{:s}_T{:s}_J{:s}_training_data_rho_output.npz".format(P, T, J)
+
+
 coupled_model = "coupled_model.json"
 harmonic_model = "harmonic_model.json"
 sampling_model = "sampling_model.json"

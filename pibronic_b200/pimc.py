@@ -462,18 +462,20 @@ class BoxData:
             raise _cabi.PbxError("no CUDA device: pibronic_b200 has no CPU path")
         return torch.cuda.current_device()
 
-    def device_plan(self, pm=None, no_scaling=False, device=None):
-        """the pbx plan (device tables) for this job; built once per (pm, scaling) variant"""
+    def device_plan(self, pm=None, no_scaling=False, device=None, rho_double_shift=False):
+        """the pbx plan (device tables) for this job; one per (flags word, device): changing a knob gives a new plan"""
         pm = self._PM if pm is None else pm
         device = self._device_index() if device is None else device
-        key = (bool(pm), bool(no_scaling), device)
+        flags = (_cabi.FLAG_PM if pm else 0)
+        flags |= _cabi.QUIRK_RHO_TRUNC if self.quirk_rho_trunc else 0
+        flags |= _cabi.FLAG_EIG_JACOBI if self.eig_jacobi else 0
+        flags |= _cabi.FLAG_FORCE_GENERIC if self.force_generic else 0
+        # the stage-by-stage API (no_scaling) always uses tau: the consistent-estimator flag only exists on the fused path
+        flags |= _cabi.FLAG_M_TAU_PM if (self.m_tau_pm and pm and not no_scaling) else 0
+        flags |= _cabi.FLAG_NO_SCALING if no_scaling else 0
+        flags |= _cabi.QUIRK_RHO_DOUBLE_SHIFT if rho_double_shift else 0
+        key = (flags, device)
         if key not in self._plans:
-            flags = (_cabi.FLAG_PM if pm else 0)
-            flags |= _cabi.QUIRK_RHO_TRUNC if self.quirk_rho_trunc else 0
-            flags |= _cabi.FLAG_EIG_JACOBI if self.eig_jacobi else 0
-            flags |= _cabi.FLAG_FORCE_GENERIC if self.force_generic else 0
-            flags |= _cabi.FLAG_M_TAU_PM if (self.m_tau_pm and pm) else 0
-            flags |= _cabi.FLAG_NO_SCALING if no_scaling else 0
             vib, rho = self.vib.raw, self.rho.raw
             self._plans[key] = _cabi.Plan(vib['energy'], vib['omega'], vib['linear'], vib['quadratic'],
                                           rho['energy'], rho['omega'], rho['linear'], self.beads, self.beta,
@@ -504,6 +506,15 @@ class BoxData:
         R = self._scratch['drawn']
         self.qTensor[:R.shape[0]] = R[:, NEW, ...]
         self.qTempTensor[:R.shape[0]] = R[:, NEW, ...]
+
+    def generate_random_R_values(self, result, storage_array, sample_view):
+        """uniform random co-ordinates in [0, 1) with no relation to rho or g, only the right dimensions (pimc.py:602-611);
+        stored in storage_array[sample_view] and published in qTensor.  The stream is numpy's PCG64 seeded with
+        (data.seed, first sample of the view): reproducible, independent of how the run is cut into blocks"""
+        n = sample_view.stop - sample_view.start
+        rng = np.random.default_rng([int(self.seed), int(self.sample_offset) + int(sample_view.start)])
+        storage_array[sample_view, :, :] = rng.random(size=(n, self.modes, self.beads))
+        self.qTensor[:n] = storage_array[sample_view, NEW, ...]
 
 
 class BoxDataPM(BoxData):
@@ -812,6 +823,52 @@ def block_compute_gR(data, result):
     result.save_results(n)
 
 
+def _eval_unscaled(data, R, rho_double_shift=False):
+    """rho(R) and g(R) WITHOUT the S scaling for caller supplied co-ordinates R (n, N, P): (2, n) host array"""
+    import torch
+    plan = data.device_plan(pm=False, no_scaling=True, rho_double_shift=rho_double_shift)
+    R = np.ascontiguousarray(R, dtype=F64)
+    out = np.empty((2, R.shape[0]))
+    with torch.cuda.device(plan.device):
+        plan.eval_coords_host(R, out4=out)
+    return out
+
+
+def save_gR_with_samples(data, result, input_R_values):
+    """g(R) with the R values it belongs to, as two .npz files next to the PIMC results (pimc.py:1250-1270):
+    ..._training_data_g_output.npz {number_of_samples, g} and ..._training_data_input.npz {number_of_samples, input_R_values}"""
+    from functools import partial
+    result.partial_name = partial(file_name.training_data_g_output().format, P=data.beads, T=data.temperature)
+    np.savez(result.compute_path_to_file(), number_of_samples=result.samples, g=result.scaled_g)
+    result.partial_name = partial(file_name.training_data_input().format, P=data.beads, T=data.temperature)
+    np.savez(result.compute_path_to_file(), number_of_samples=result.samples, input_R_values=input_R_values)
+
+
+def block_compute_rhoR_from_input_samples(data, result, input_R_values, quirk_double_shift=False):
+    """rho(R), not scaled, for caller supplied co-ordinates input_R_values (X, N, P) -> result.scaled_rho[0:blocks*block_size];
+    the caller saves the results (pimc.py:1273-1302).  One launch on the device instead of the block loop.
+
+    quirk_double_shift=True reproduces the reference, which subtracts the SYSTEM's shift from the co-ordinates and then
+    the sampling model's (pimc.py:1293-1298): rho evaluated at R - d_vib[a] - d_rho[a]; it needs
+    A_rho == A (the reference reads stale scratch otherwise).  Default: rho at the co-ordinates given."""
+    n = int(data.blocks) * int(data.block_size)
+    assert 0 < n <= result.samples and input_R_values.shape[0] >= n, "blocks*block_size must be in (0, samples]"
+    result.scaled_rho[:n] = _eval_unscaled(data, input_R_values[:n], rho_double_shift=quirk_double_shift)[0]
+
+
+def block_compute_gR_from_raw_samples(data, result):
+    """g(R), not scaled, on uniform random co-ordinates that were NOT sampled from rho, saved with those co-ordinates
+    (pimc.py:1305-1338: training sets for ML models)"""
+    n = int(data.blocks) * int(data.block_size)
+    assert 0 < n <= result.samples, "blocks*block_size must be in (0, samples]"
+    input_R_values = np.empty(data.size['XNP'], dtype=F64)
+    for block_index in range(int(data.blocks)):
+        view = slice(block_index * data.block_size, (block_index + 1) * data.block_size)
+        data.generate_random_R_values(result, input_R_values, view)
+    result.scaled_g[:n] = _eval_unscaled(data, input_R_values[:n])[1]
+    save_gR_with_samples(data, result, input_R_values)
+
+
 def block_compute(data, result):
     """numerator g and denominator rho for blocks*block_size sampled points; saves the .npz"""
     end = _compute_on_device(data, result, pm=False)
@@ -824,3 +881,60 @@ def block_compute_pm(data, result):
     assert isinstance(result, BoxResultPM), "incorrect object type"
     end = _compute_on_device(data, result, pm=True)
     result.save_results(end)
+
+
+def simple_wrapper(id_data, id_rho=0, path_root='/work/ngraymon/pimc/', states=2, modes=2, beads=1000):
+    """Just do simple expval(Z) calculation (pimc.py:1465-1497): 100 samples in one block at 300 K; the reference's
+    hard-coded root directory, surfaces, modes and beads are the defaults of the keyword arguments"""
+    samples = int(1e2)
+    Bsize = int(1e2)
+    data = BoxData()
+    data.seed = 232942   # the reference seeds numpy with this number
+    data.id_data = id_data
+    data.id_rho = id_rho
+    files = file_structure.FileStructure(path_root, id_data, id_rho)
+    data.path_vib_model = files.path_vib_model
+    data.path_rho_model = files.path_rho_model
+    data.states = states
+    data.modes = modes
+    data.samples = samples
+    data.beads = beads
+    data.temperature = 300.0
+    data.blocks = samples // Bsize
+    data.block_size = Bsize
+    files.generate_model_hashes()
+    data.hash_vib, data.hash_rho = files.hash_vib, files.hash_rho
+    data.preprocess()
+    results = BoxResult(data=data)
+    results.path_root = files.path_rho_results
+    block_compute(data, results)
+    data.release()
+    return results
+
+
+def plus_minus_wrapper(id_data, id_rho=0, path_root='/work/ngraymon/pimc/', states=3, modes=6, beads=20):
+    """Calculate all the possible temp +/- approaches (pimc.py:1500-1535): 100 samples in one block at 300 K"""
+    samples = int(1e2)
+    Bsize = int(1e2)
+    data = BoxDataPM(constants.delta_beta)
+    data.seed = 232942
+    data.id_data = id_data
+    data.id_rho = id_rho
+    files = file_structure.FileStructure(path_root, id_data, id_rho)
+    data.path_vib_model = files.path_vib_model
+    data.path_rho_model = files.path_rho_model
+    data.states = states
+    data.modes = modes
+    data.samples = samples
+    data.beads = beads
+    data.temperature = 300.00
+    data.blocks = samples // Bsize
+    data.block_size = Bsize
+    files.generate_model_hashes()
+    data.hash_vib, data.hash_rho = files.hash_vib, files.hash_rho
+    data.preprocess()
+    results = BoxResultPM(data=data)
+    results.path_root = files.path_rho_results
+    block_compute_pm(data, results)
+    data.release()
+    return results

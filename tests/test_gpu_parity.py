@@ -616,6 +616,80 @@ def test_block_compute_gR_is_unscaled(cuda, tmp_path):
     data.release()
 
 
+def _small_job(tmp_path, pm=False, samples=200, block=100, beads=12):
+    from pibronic_b200 import file_structure, pimc, synthetic
+    FS = file_structure.FileStructure(tmp_path, 0, 0)
+    synthetic.write_data_set(FS, synthetic.coupled_model(2, 2, (0.02, 0.04), (0.1, 0.2), seed=3, linear=0.05))
+    FS.generate_model_hashes()
+    data = (pimc.BoxDataPM if pm else pimc.BoxData).from_FileStructure(FS)
+    data.samples, data.beads, data.temperature, data.block_size, data.blocks = samples, beads, 300.0, block, samples // block
+    data.hash_vib, data.hash_rho, data.seed = FS.hash_vib, FS.hash_rho, 7
+    data.preprocess()
+    result = (pimc.BoxResultPM if pm else pimc.BoxResult)(data=data)
+    result.path_root, result.id_job = FS.path_rho_results, 0
+    return FS, data, result
+
+
+def test_block_compute_rhoR_from_input_samples(cuda, tmp_path):
+    """pimc.py:1273-1302: rho(R), not scaled, on caller supplied co-ordinates -- the oracle's denominator on the same R;
+    with quirk_double_shift the reference's own arithmetic (q = R - d_vib[a] - d_rho[a])"""
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import pimc
+    FS, data, result = _small_job(tmp_path)
+    rng = np.random.default_rng(5)
+    R = rng.normal(scale=0.15, size=(200, 2, 12))
+    pimc.block_compute_rhoR_from_input_samples(data, result, R)
+    tab = orc.precompute(orc.load_vibronic_json(FS.path_vib_model), orc.load_sampling_json(FS.path_rho_model), 12, 300.0)
+    want = orc.denominator(orc.o_factors(R, tab.d_rho, tab.rho))
+    assert rel_err(result.scaled_rho, want) < RTOL and np.isnan(result.scaled_g).all()
+    pimc.block_compute_rhoR_from_input_samples(data, result, R, quirk_double_shift=True)
+    quirk = orc.denominator(orc.o_factors(R, tab.d_rho + tab.d_vib, tab.rho))
+    assert rel_err(result.scaled_rho, quirk) < RTOL
+    assert rel_err(quirk, want) > 1e-3          # the two conventions really differ on this model
+    data.release()
+
+
+def test_block_compute_gR_from_raw_samples(cuda, tmp_path):
+    """pimc.py:1305-1338 + save_gR_with_samples 1250-1270: unscaled g on uniform random co-ordinates, saved with them"""
+    from os.path import join
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import pimc
+    FS, data, result = _small_job(tmp_path)
+    pimc.block_compute_gR_from_raw_samples(data, result)
+    g_file = np.load(join(FS.path_rho_results, "P12_T300.00_J0_training_data_g_output.npz"))
+    r_file = np.load(join(FS.path_rho_results, "P12_T300.00_J0_training_data_input.npz"))
+    assert int(g_file["number_of_samples"]) == 200 and int(r_file["number_of_samples"]) == 200
+    R = r_file["input_R_values"]
+    assert R.shape == (200, 2, 12) and R.min() >= 0.0 and R.max() < 1.0
+    tab = orc.precompute(orc.load_vibronic_json(FS.path_vib_model), orc.load_sampling_json(FS.path_rho_model), 12, 300.0)
+    _, g = orc.estimate_block(tab, R, pm=False, faithful=False, scale=False)
+    assert rel_err(g_file["g"], g) < RTOL and np.array_equal(g_file["g"], result.scaled_g)
+    # same seed -> same co-ordinates, whatever the block size
+    (tmp_path / "again").mkdir()
+    FS2, data2, result2 = _small_job(tmp_path / "again", block=50)
+    pimc.block_compute_gR_from_raw_samples(data2, result2)
+    assert np.array_equal(result2.scaled_g[:50], result.scaled_g[:50])
+    data.release()
+    data2.release()
+
+
+def test_simple_and_plus_minus_wrappers(cuda, tmp_path):
+    """pimc.py:1465-1535: the two convenience drivers (100 samples, one block) write the reference's result files"""
+    from os.path import isfile, join
+    from pibronic_b200 import file_structure, pimc, synthetic
+    FS = file_structure.FileStructure(tmp_path, 4, 0)
+    synthetic.write_data_set(FS, synthetic.coupled_model(2, 2, (0.02, 0.04), (0.1, 0.2), seed=3, linear=0.05))
+    res = pimc.simple_wrapper(4, path_root=str(tmp_path), beads=16)
+    assert isfile(join(FS.path_rho_results, "P16_T300.00_J0_data_points.npz"))
+    assert res.samples == 100 and np.all(np.isfinite(res.scaled_g / res.scaled_rho))
+    FS3 = file_structure.FileStructure(tmp_path, 5, 0)
+    synthetic.write_data_set(FS3, synthetic.coupled_model(3, 6, (0.02, 0.04), (0.1, 0.2), seed=4, linear=0.05))
+    res = pimc.plus_minus_wrapper(5, path_root=str(tmp_path))
+    loaded = pimc.BoxResultPM()
+    loaded.load_multiple_results([join(FS3.path_rho_results, "P20_T300.00_J0_data_points.npz")])
+    assert loaded.samples == 100 and np.array_equal(loaded.scaled_gofr_plus, res.scaled_gofr_plus)
+
+
 def test_device_math(cuda):
     """the branch-free log / sqrt / exp / sincos of pbx_device.cuh against numpy, in units of ulp"""
     rng = np.random.default_rng(0)
