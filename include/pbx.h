@@ -183,6 +183,12 @@ int pbx_block_sums_dev(pbx_plan *plan, const double *out4_dev, int64_t n_samples
 int pbx_stats_dev(pbx_plan *plan, const double *out4_dev, int64_t n_samples, double *stats_host, void *stream);
 int pbx_stats_host(pbx_plan *plan, const double *out4_host, int64_t ld_host, int64_t n_samples, double *stats_host);
 int pbx_stats_last(pbx_plan *plan, double *stats_host);
+/* Plan-free forms: the statistics depend on (beta, delta_beta) only.  out4 is [4][n] (row stride n / ld_host) on `device`
+ * (pbx_stats_arrays_dev; synchronises `stream`) or on the host (pbx_stats_arrays_host: uploaded first). */
+int pbx_stats_arrays_dev(const double *out4_dev, int64_t n_samples, double beta, double delta_beta, int32_t device,
+                         double *stats_host, void *stream);
+int pbx_stats_arrays_host(const double *out4_host, int64_t ld_host, int64_t n_samples, double beta, double delta_beta,
+                          int32_t device, double *stats_host);
 
 /* Self-test hook for the branch-free device math used by the kernels (pbx_device.cuh):
  * kind 0 ln(x) for x in (0,1], 1 sqrt(x), 2 exp(x) for x <= 0, 3 sin(2 pi x), 4 cos(2 pi x) for x in [0,1). */

@@ -85,6 +85,8 @@ def lib():
         "pbx_stats_dev": (C.c_int, [vp, vp, i64, _dp, vp]),
         "pbx_stats_host": (C.c_int, [vp, vp, i64, i64, _dp]),
         "pbx_stats_last": (C.c_int, [vp, _dp]),
+        "pbx_stats_arrays_dev": (C.c_int, [vp, i64, dbl, dbl, i32, _dp, vp]),
+        "pbx_stats_arrays_host": (C.c_int, [vp, i64, i64, dbl, dbl, i32, _dp]),
         "pbx_math_probe_dev": (C.c_int, [i32, vp, vp, i64, vp]),
         "pbx_fp64_peak_tflops": (C.c_int, [i32, _dp]),
         "pbx_fp64_peak_tflops_kind": (C.c_int, [i32, i32, _dp]),
@@ -100,7 +102,7 @@ EXPORTED_SYMBOLS = ("pbx_abi_version", "pbx_last_error", "pbx_device_count", "pb
                     "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_kernel_path", "pbx_plan_launch_count", "pbx_plan_launch_param_bytes", "pbx_sample_eval_dev",
                     "pbx_sample_eval_host", "pbx_eval_coords_dev", "pbx_eval_coords_host", "pbx_sample_coords_dev",
                     "pbx_eval_stages_dev", "pbx_chain_trace_dev", "pbx_block_sums_dev", "pbx_stats_dev", "pbx_stats_host",
-                    "pbx_stats_last", "pbx_math_probe_dev", "pbx_fp64_peak_tflops", "pbx_fp64_peak_tflops_kind")
+                    "pbx_stats_last", "pbx_stats_arrays_dev", "pbx_stats_arrays_host", "pbx_math_probe_dev", "pbx_fp64_peak_tflops", "pbx_fp64_peak_tflops_kind")
 
 
 def _check(rc):
@@ -285,6 +287,23 @@ class Plan:
         assert out4.shape[0] == 4 or not self.pm
         _check(lib().pbx_eval_coords_host(self._handle, R.ctypes.data, int(n), out4.ctypes.data, int(ld)))
         return out4
+
+
+def stats_arrays_host(out4, beta, delta_beta, device=0):
+    """Z, E, Cv + jackknife (STAT_NAMES) of a host (4, n) array; no plan needed: only beta and delta_beta enter"""
+    assert out4.dtype == np.float64 and out4.ndim == 2 and out4.shape[0] == 4 and out4.strides[1] == 8
+    values = (C.c_double * NSTATS)()
+    _check(lib().pbx_stats_arrays_host(out4.ctypes.data, out4.strides[0] // 8, int(out4.shape[1]), float(beta),
+                                       float(delta_beta), int(device), values))
+    return dict(zip(STAT_NAMES, (float(v) for v in values)))
+
+
+def stats_arrays_dev(out4, beta, delta_beta, stream=None):
+    """the same from a contiguous CUDA tensor (4, n)"""
+    values = (C.c_double * NSTATS)()
+    _check(lib().pbx_stats_arrays_dev(_devptr(out4), int(out4.shape[1]), float(beta), float(delta_beta),
+                                      int(out4.device.index or 0), values, _stream_handle(stream)))
+    return dict(zip(STAT_NAMES, (float(v) for v in values)))
 
 
 def device_count():

@@ -847,26 +847,24 @@ int pbx_eval_coords_host(pbx_plan* p, const double* R_host, int64_t n, double* o
     return PBX_OK;
 }
 
-int pbx_stats_dev(pbx_plan* p, const double* out4, int64_t n, double* stats_host, void* stream) {
-    if (!p || !out4 || !stats_host) return fail(PBX_ERR_ARG, "null argument");
-    if (n < 2) return fail(PBX_ERR_ARG, "statistics need at least 2 samples");
-    if (!p->pm) return fail(PBX_ERR_ARG, "statistics need a PBX_FLAG_PM plan (g+ and g-)");
-    PBX_NEED_DEVICE(p);
-    DeviceGuard guard(p->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!p->stat_partials) PBX_CUDA(cudaMalloc((void**)&p->stat_partials, kStatGrid * 4 * sizeof(double)));
-    const double db = p->H.delta_beta, inv2db = 1.0 / (2.0 * db), invdb2 = 1.0 / (db * db);
+}  // extern "C"
+
+namespace {
+// Z, E, Cv and their leave-one-out jackknife from a device [4][n] array; needs only (beta, delta_beta).
+// `partials` is a device buffer of kStatGrid * 4 doubles.  Synchronises `st`.
+int stats_core(const double* out4, int64_t n, double beta, double db, double* partials, double* stats_host, cudaStream_t st) {
+    const double inv2db = 1.0 / (2.0 * db), invdb2 = 1.0 / (db * db);
     const double kB = 1.38064852e-23 / 1.6021766208e-19;        // pibronic/constants.py:12,24
-    const double T = 1.0 / (kB * p->H.beta), kbt2 = kB * T * T;
+    const double T = 1.0 / (kB * beta), kbt2 = kB * T * T;
     double part[kStatGrid * 4];
     auto total = [&](int col) {
         long double acc = 0.0L;
         for (int b = 0; b < kStatGrid; ++b) acc += part[b * 4 + col];
         return acc;
     };
-    pbx_stat_sums_kernel<<<kStatGrid, 256, 0, st>>>(out4, n, n, inv2db, invdb2, p->stat_partials);
+    pbx_stat_sums_kernel<<<kStatGrid, 256, 0, st>>>(out4, n, n, inv2db, invdb2, partials);
     PBX_CUDA(cudaGetLastError());
-    PBX_CUDA(cudaMemcpyAsync(part, p->stat_partials, sizeof(part), cudaMemcpyDeviceToHost, st));
+    PBX_CUDA(cudaMemcpyAsync(part, partials, sizeof(part), cudaMemcpyDeviceToHost, st));
     PBX_CUDA(cudaStreamSynchronize(st));
     const long double X = (long double)n, S_r = total(0), S_rr = total(1), S_1 = total(2), S_2 = total(3);
     const long double Z = S_r / X;
@@ -875,11 +873,10 @@ int pbx_stats_dev(pbx_plan* p, const double* out4, int64_t n, double* stats_host
     const long double E = -(S_1 / X) / Z;
     const long double Cv = ((S_2 / X) / Z - E * E) / kbt2;
     pbx_jackknife_kernel<<<kStatGrid, 256, 0, st>>>(out4, n, n, inv2db, invdb2, (double)S_r, (double)S_1, (double)S_2,
-                                                   1.0 / kbt2, (double)E, (double)Cv, p->stat_partials);
+                                                   1.0 / kbt2, (double)E, (double)Cv, partials);
     PBX_CUDA(cudaGetLastError());
-    PBX_CUDA(cudaMemcpyAsync(part, p->stat_partials, sizeof(part), cudaMemcpyDeviceToHost, st));
+    PBX_CUDA(cudaMemcpyAsync(part, partials, sizeof(part), cudaMemcpyDeviceToHost, st));
     PBX_CUDA(cudaStreamSynchronize(st));
-    p->launches += 2;
     const long double sE = total(0), sEE = total(1), sC = total(2), sCC = total(3);
     const long double mean_fE = (long double)(double)E + sE / X, mean_fC = (long double)(double)Cv + sC / X;
     long double var_fE = (sEE - sE * sE / X) / (X - 1), var_fC = (sCC - sC * sC / X) / (X - 1);
@@ -894,6 +891,53 @@ int pbx_stats_dev(pbx_plan* p, const double* out4, int64_t n, double* stats_host
     stats_host[8] = (double)(X * Cv - (X - 1) * mean_fC);
     stats_host[9] = (double)(std::sqrt(X - 1) * std::sqrt(var_fC));
     return PBX_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int pbx_stats_dev(pbx_plan* p, const double* out4, int64_t n, double* stats_host, void* stream) {
+    if (!p || !out4 || !stats_host) return fail(PBX_ERR_ARG, "null argument");
+    if (n < 2) return fail(PBX_ERR_ARG, "statistics need at least 2 samples");
+    if (!p->pm) return fail(PBX_ERR_ARG, "statistics need a PBX_FLAG_PM plan (g+ and g-)");
+    PBX_NEED_DEVICE(p);
+    DeviceGuard guard(p->device);
+    if (!p->stat_partials) PBX_CUDA(cudaMalloc((void**)&p->stat_partials, kStatGrid * 4 * sizeof(double)));
+    p->launches += 2;
+    return stats_core(out4, n, p->H.beta, p->H.delta_beta, p->stat_partials, stats_host, (cudaStream_t)stream);
+}
+
+// plan-free forms: statistics need (beta, delta_beta) only
+int pbx_stats_arrays_dev(const double* out4, int64_t n, double beta, double delta_beta, int32_t device, double* stats_host,
+                         void* stream) {
+    if (!out4 || !stats_host) return fail(PBX_ERR_ARG, "null argument");
+    if (n < 2) return fail(PBX_ERR_ARG, "statistics need at least 2 samples");
+    if (!(beta > 0) || !(delta_beta > 0)) return fail(PBX_ERR_ARG, "need beta > 0 and delta_beta > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PBX_ERR_CUDA, "no CUDA device available: pbx has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(PBX_ERR_ARG, "device index out of range");
+    DeviceGuard guard(device);
+    double* partials = nullptr;
+    PBX_CUDA(cudaMalloc((void**)&partials, kStatGrid * 4 * sizeof(double)));
+    const int rc = stats_core(out4, n, beta, delta_beta, partials, stats_host, (cudaStream_t)stream);
+    cudaFree(partials);
+    return rc;
+}
+
+int pbx_stats_arrays_host(const double* out4_host, int64_t ld_host, int64_t n, double beta, double delta_beta, int32_t device,
+                          double* stats_host) {
+    if (!out4_host || !stats_host) return fail(PBX_ERR_ARG, "null argument");
+    if (n < 2 || ld_host < n) return fail(PBX_ERR_ARG, "need n >= 2 and ld_host >= n");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PBX_ERR_CUDA, "no CUDA device available: pbx has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(PBX_ERR_ARG, "device index out of range");
+    DeviceGuard guard(device);
+    double* dev = nullptr;
+    PBX_CUDA(cudaMalloc((void**)&dev, (size_t)4 * n * sizeof(double)));
+    cudaError_t e = cudaMemcpy2D(dev, n * sizeof(double), out4_host, ld_host * sizeof(double), n * sizeof(double), 4, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? pbx_stats_arrays_dev(dev, n, beta, delta_beta, device, stats_host, nullptr) : cuda_fail(e, "cudaMemcpy2D");
+    cudaFree(dev);
+    return rc;
 }
 
 int pbx_stats_host(pbx_plan* p, const double* out4_host, int64_t ld_host, int64_t n, double* stats_host) {

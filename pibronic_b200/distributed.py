@@ -84,18 +84,23 @@ def block_compute_sharded(data, result, group=None, gather=False, save=True, com
     bs = int(data.block_size)
     first, n = first_block * bs, n_blocks * bs
     names = ("scaled_rho", "scaled_g", "scaled_gofr_plus", "scaled_gofr_minus")
+    rows = 4 if isinstance(result, BoxResultPM) else 2       # from the result type on EVERY rank, also one without blocks
+    use_cuda = world > 1 and dist.get_backend(group) == "nccl"
+    device = None
+    if use_cuda:
+        # the collectives run on the GPU the plan computes on (LOCAL_RANK / data.device), whatever the current device is
+        device = torch.device("cuda", data._device_index())
+        torch.cuda.set_device(device)
     if n:
         out, sums = compute_fn(data, first, n)
-        for k in range(out.shape[0]):
+        assert out.shape[0] == rows, f"compute_fn returned {out.shape[0]} rows for a {type(result).__name__}"
+        for k in range(rows):
             getattr(result, names[k])[first:first + n] = out[k]
     else:
-        out, sums = np.empty((4, 0)), np.empty((0, _cabi.NSUMS))
-    use_cuda = world > 1 and dist.get_backend(group) == "nccl"
-    device = torch.device("cuda", torch.cuda.current_device()) if use_cuda else None
+        out, sums = np.empty((rows, 0)), np.empty((0, _cabi.NSUMS))
     result.block_sums = reduce_block_sums(sums, first_block, int(data.blocks), group=group, device=device)
 
     if gather and world > 1:
-        rows = out.shape[0]
         total = int(data.blocks) * bs
         full = torch.zeros((rows, total), dtype=torch.float64, device=device or "cpu")
         if n:
@@ -114,7 +119,7 @@ def block_compute_sharded(data, result, group=None, gather=False, save=True, com
             shard = shard_cls(X=n)
             shard.partial_name, shard.path_root = result.partial_name, result.path_root
             shard.hash_vib, shard.hash_rho, shard.id_job = result.hash_vib, result.hash_rho, base + rank
-            for k in range(out.shape[0]):
+            for k in range(rows):
                 getattr(shard, names[k])[:] = out[k]
             shard.save_results(n)
     return result

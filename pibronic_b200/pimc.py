@@ -880,6 +880,7 @@ def block_compute_pm(data, result):
     assert isinstance(data, BoxDataPM), "incorrect object type"
     assert isinstance(result, BoxResultPM), "incorrect object type"
     end = _compute_on_device(data, result, pm=True)
+    result.delta_beta = data.delta_beta      # the finite-difference step these g+- belong to (read by pibronic_b200.stats)
     result.save_results(end)
 
 

@@ -26,21 +26,17 @@ def add_harmonic_contribution(input_dict, E_sampling, Cv_sampling):
     input_dict["Cv"] += Cv_sampling
 
 
-def _stats_plan(temperature, device=None):
-    """a model-free plan is not possible: statistics only need beta and delta_beta, so a trivial 1x1 model
-    carries them (the estimator tables are never used)"""
+def _device_statistics(temperature, pimc_result, delta_beta=None, device=None):
+    """the ten numbers of pbx_stats_arrays_host for a BoxResultPM (host arrays are uploaded once).  The finite-difference
+    step is `delta_beta`, else the one the result object carries (BoxResultPM.delta_beta, set by block_compute_pm and
+    stored in the .npz), else constants.delta_beta (what the reference's stats always assume, stats.py:38-55)"""
     import torch
     if device is None:
         if not torch.cuda.is_available():
             raise _cabi.PbxError("no CUDA device: pibronic_b200 has no CPU path")
         device = torch.cuda.current_device()
-    one = np.ones(1)
-    return _cabi.Plan(np.zeros((1, 1)), one, None, None, np.zeros(1), one, None, 3, constants.beta(temperature),
-                      constants.delta_beta, flags=_cabi.FLAG_PM, device=device)
-
-
-def _device_statistics(temperature, pimc_result):
-    """the ten numbers of pbx_stats_* for a BoxResultPM (host arrays are uploaded once)"""
+    if delta_beta is None:
+        delta_beta = getattr(pimc_result, "delta_beta", None) or constants.delta_beta
     store = getattr(pimc_result, "_store", None)
     n = int(pimc_result.samples)
     rows = (pimc_result.scaled_rho, pimc_result.scaled_g, pimc_result.scaled_gofr_plus, pimc_result.scaled_gofr_minus)
@@ -48,11 +44,7 @@ def _device_statistics(temperature, pimc_result):
         host = store
     else:
         host = np.stack([np.asarray(r, dtype=np.float64) for r in rows])
-    plan = _stats_plan(temperature)
-    try:
-        return plan.stats_host(host)
-    finally:
-        plan.close()
+    return _cabi.stats_arrays_host(host, constants.beta(temperature), delta_beta, device)
 
 
 def basic_statistical_analysis(temperature, pimc_result, analytic_data):
@@ -75,7 +67,7 @@ def basic_jackknife_analysis(temperature, pimc_result, analytic_data):
     return output_dict
 
 
-def consistent_jackknife_analysis(temperature, pimc_result, analytic_data=None):
+def consistent_jackknife_analysis(temperature, pimc_result, analytic_data=None, delta_beta=None):
     """NOT in the reference.  For results computed with ``data.m_tau_pm = True`` (PBX_FLAG_M_TAU_PM: g+- built with
     exp(-tau+- V)) the finite differences of g already carry the whole beta dependence of Z = Z_rho <g/rho>:
 
@@ -85,8 +77,9 @@ def consistent_jackknife_analysis(temperature, pimc_result, analytic_data=None):
     adds E and Cv of the sampling model (stats.py:126-130); on the reference's own test model data_set_1 that gives
     E = +0.104, Cv = 3.7e-3 against the sum-over-states values -0.4233 and 1.53e-4, which this estimator reproduces
     within its jackknife error (tests/test_gpu_parity.py::test_pimc_reproduces_the_sum_over_states_thermodynamics).
-    If `analytic_data` has "Z" (the sampling model's partition function) Z is returned in absolute units."""
-    out = _device_statistics(temperature, pimc_result)
+    If `analytic_data` has "Z" (the sampling model's partition function) Z is returned in absolute units.
+    `delta_beta` must be the step the results were computed with (default: the one recorded in the result object)."""
+    out = _device_statistics(temperature, pimc_result, delta_beta=delta_beta)
     if analytic_data is not None and "Z" in analytic_data:
         out["Z"] *= analytic_data["Z"]
         out["Z error"] *= analytic_data["Z"]

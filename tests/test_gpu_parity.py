@@ -588,6 +588,31 @@ def test_sweep_statistics_and_thermo_files(cuda, tmp_path):
         assert stored["Z"] > 0 and stored["Z error"] < 0.05 * stored["Z"]
     # colder -> lower energy
     assert thermo[(12, 250.0)]["E"] < thermo[(12, 300.0)]["E"]
+    # numbers, not only files: (i) per-sample values of one point against the oracle on the co-ordinates the device
+    # sampler reports for the sweep's seed; (ii) the thermo file against the numpy restatement of the reference's
+    # basic_jackknife_analysis (oracle/stats_oracle.py) on the arrays of the .npz + the analytic sampling-model data
+    from oracle import pimc_oracle as orc, stats_oracle
+    from pibronic_b200 import pimc, postprocessing as pp
+    P, T = 8, 250.0
+    data = pimc.BoxDataPM.from_FileStructure(FS)
+    data.samples, data.beads, data.temperature, data.block_size, data.blocks = 20000, P, T, 1000, 20
+    data.seed = 11
+    data.preprocess()
+    data.draw_sample(slice(0, 200))
+    data.transform_sampled_coordinates(slice(0, 200))
+    R = np.ascontiguousarray(data.qTensor[:200, 0])
+    data.release()
+    tab = orc.precompute(orc.load_vibronic_json(FS.path_vib_model), orc.load_sampling_json(FS.path_rho_model), P, T)
+    want = oracle_eval(tab, R)
+    res = results[(P, T)]
+    got = np.stack([res.scaled_rho[:200], res.scaled_g[:200], res.scaled_gofr_plus[:200], res.scaled_gofr_minus[:200]])
+    assert rel_err(got, want) < RTOL
+    rho_data = {}
+    pp.load_analytic_data(FS, T, rho_data)
+    numpy_stats = stats_oracle.basic_jackknife_analysis(T, res.scaled_rho, res.scaled_g, res.scaled_gofr_plus, res.scaled_gofr_minus,
+                                                        rho_data["E"], rho_data["Cv"])
+    for key in ("Z", "Z error", "E", "Cv", "jk_E", "jk_E error", "jk_Cv", "jk_Cv error"):
+        assert np.isclose(thermo[(P, T)][key], numpy_stats[key], rtol=1e-7, atol=1e-14), key
     with pytest.raises(Exception, match="Invalid value for parameter method"):
         stats.statistical_analysis_of_pimc(FS, method="alpha")
 
