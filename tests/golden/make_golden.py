@@ -154,6 +154,27 @@ def pack_stats_kat():
     print("stats_kat.npz:", {k: float(v) for k, v in expected.items()})
 
 
+def pack_c5_stats():
+    """BASELINE.json configs[4]: c2 model sampled from the alternate rho (cases/c5_altrho), P=64, 64 blocks of 100 samples,
+    run through the unmodified reference; Z, E, Cv and their jackknife errors from the reference's own
+    basic_jackknife_analysis (harmonic contribution of the sampling model left out: E_sampling = Cv_sampling = 0)"""
+    from pibronic.stats import stats as ref_stats
+    case_dir = join(HERE, "cases", "c5_altrho")
+    P, T, blocks, B = 64, 300.0, 64, 100
+    out = run_reference(join(case_dir, "coupled_model.json"), join(case_dir, "sampling_model.json"),
+                        P=P, T=T, X=blocks * B, B=B, seed=64)
+
+    class Holder:
+        pass
+    res = Holder()
+    res.scaled_rho, res.scaled_g, res.scaled_gofr_plus, res.scaled_gofr_minus = (out[k] for k in ("s_rho", "s_g", "s_gP", "s_gM"))
+    res.samples = blocks * B
+    expected = ref_stats.basic_jackknife_analysis(T, res, {"E": 0.0, "Cv": 0.0})
+    np.savez_compressed(join(HERE, "c5_stats.npz"), P=P, T=T, blocks=blocks, block_size=B,
+                        keys=np.array(sorted(expected)), values=np.array([expected[k] for k in sorted(expected)]))
+    print("c5_stats.npz:", {k: float(v) for k, v in expected.items()})
+
+
 def main():
     pack_explicit_kat()
     pack_stats_kat()
@@ -181,6 +202,7 @@ def main():
     # c5: c2 model sampled from a different rho (the un-rotated diagonal model)
     rng_free = synthetic.coupled_model(4, 6, (0.14, 0.45), (10.3, 10.9), mixing=0.0, quadratic=0.0)
     write_case("c5_altrho", c2, synthetic.diagonal_of(rng_free), P=16, T=300.0, X=16, B=8, seed=17)
+    pack_c5_stats()
 
 
 if __name__ == "__main__":

@@ -104,3 +104,38 @@ def test_two_rank_sharding_matches_single_process(tmp_path, gather):
         merged.load_multiple_results(paths)
         assert merged.samples == 28
         assert np.array_equal(np.sort(merged.scaled_gofr_plus), np.sort(full[2]))
+
+
+def _fake_compute_two_rows(data, first, n):
+    out, sums = _fake_compute(data, first, n)
+    return out[:2], sums
+
+
+def _worker_idle_rank(rank, world, port, root):
+    import torch.distributed as dist
+    from pibronic_b200 import pimc
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Data:
+        blocks, block_size, samples, beads, temperature, sample_offset = 2, 4, 8, 12, 300.0, 0
+        hash_vib, hash_rho = "hv", "hr"
+    result = pimc.BoxResult(data=Data)              # the non-PM container: two rows
+    result.path_root, result.id_job = root, 0
+    distributed.block_compute_sharded(Data, result, gather=True, compute_fn=_fake_compute_two_rows)
+    np.save(join(root, f"g_idle_{rank}.npy"), result.scaled_g)
+    dist.destroy_process_group()
+
+
+def test_rank_without_blocks_and_two_row_results(tmp_path):
+    """more ranks than blocks: the idle rank takes part in the collectives with the row count of the result TYPE
+    (a BoxResult has two rows, no g+-), and every rank ends up with the gathered arrays"""
+    import torch.multiprocessing as mp
+    world = 3
+    mp.spawn(_worker_idle_rank, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+
+    class Data:
+        blocks, block_size, sample_offset = 2, 4, 0
+    full, _ = _fake_compute(Data, 0, 8)
+    for rank in range(world):
+        assert np.array_equal(np.load(join(tmp_path, f"g_idle_{rank}.npy")), full[1])

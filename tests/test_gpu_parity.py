@@ -356,6 +356,34 @@ def test_estimators_agree_with_reference_sampler_within_error(cuda):
     plan.close()
 
 
+def test_c5_block_estimators_agree_with_the_reference_run(cuda):
+    """BASELINE.json configs[4]: c2 model sampled from another rho, P=64, jackknife Z / E / Cv over 64 blocks.  The
+    reference's own run (64 blocks x 100 samples, tests/golden/c5_stats.npz made by make_golden.py::pack_c5_stats) and
+    this path (64 blocks x 1e4 samples, independent Philox draws) must agree within their combined jackknife errors"""
+    from os.path import join
+    from conftest import GOLDEN, GoldenCase
+    from oracle import pimc_oracle as orc
+    kat = np.load(join(GOLDEN, "c5_stats.npz"))
+    ref = dict(zip([str(k) for k in kat["keys"]], kat["values"]))
+    P, T, blocks = int(kat["P"]), float(kat["T"]), int(kat["blocks"])
+    case = GoldenCase("c5_altrho")
+    plan = _cabi.Plan(case.vib["E"], case.vib["w"], case.vib["L"], case.vib["Q"], case.rho["E"], case.rho["w"],
+                      case.rho["L"], P, orc.beta_of(T), orc.DELTA_BETA, flags=_cabi.FLAG_PM, device=0)
+    B = 10_000
+    out, sums = plan.sample_eval_host(64, 0, blocks * B, block_size=B)
+    mine = plan.stats_last()
+    assert sums.shape == (blocks, _cabi.NSUMS)
+    for value, error in (("Z", "Z error"), ("jk_E", "jk_E error"), ("jk_Cv", "jk_Cv error")):
+        sigma = np.hypot(mine[error], ref[error])
+        assert abs(mine[value] - ref[value]) < 4.5 * sigma, (value, mine[value], ref[value], sigma)
+        assert mine[error] < ref[error]                      # 100x the samples: smaller error bars
+    # the 64 block means scatter around the global mean as their standard error says
+    block_Z = sums[:, 0] / B
+    assert abs(block_Z.mean() - mine["Z"]) < 1e-12 * abs(mine["Z"]) + 1e-15
+    assert 0.5 < block_Z.std(ddof=1) / (mine["Z error"] * np.sqrt(blocks)) < 2.0
+    plan.close()
+
+
 def test_mixture_frequencies_and_bead_covariance_on_device(cuda):
     from conftest import GoldenCase
     case = GoldenCase("jt_rho4")

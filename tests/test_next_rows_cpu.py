@@ -95,3 +95,58 @@ def test_result_file_discovery(tmp_path):
     merged = pimc.BoxResultPM()
     pp.load_pimc_data(FS, 12, 300.0, merged)
     assert merged.samples == 8 and sorted(set(merged.scaled_g)) == [1.0, 2.0]
+
+
+# ------------------------------------------------------------------ the reference's own readers consume our files
+def _staged_reference():
+    import sys
+    from os.path import abspath, dirname
+    sys.path.insert(0, dirname(dirname(abspath(__file__))))
+    from baseline import ref_runner
+    if not ref_runner.available():
+        pytest.skip("baseline/_ref not staged (python baseline/stage_reference.py in the build container)")
+    return ref_runner.import_reference()
+
+
+def test_reference_loader_and_jackknife_consume_files_written_here(tmp_path):
+    """f2: .npz shards written by pibronic_b200.pimc.BoxResultPM.save_results load in the UNMODIFIED reference's
+    BoxResultPM.load_multiple_results (pimc.py:975-1040), and its basic_jackknife_analysis (stats.py:271-299) on them gives
+    what pibronic_b200's numpy restatement gives"""
+    ref_pimc, _ = _staged_reference()
+    from pibronic.stats import stats as ref_stats
+    from pibronic_b200 import pimc
+
+    class Data:
+        samples, beads, temperature, hash_vib, hash_rho = 600, 12, 300.0, "a" * 128, "b" * 128
+    rng = np.random.RandomState(4)
+    paths, parts = [], []
+    for job in range(2):
+        res = pimc.BoxResultPM(data=Data)
+        res.path_root, res.id_job = str(tmp_path), job
+        res.scaled_rho[:] = rng.uniform(0.5, 1.5, 600)
+        res.scaled_g[:] = res.scaled_rho * rng.uniform(1.0, 2.0, 600)
+        res.scaled_gofr_plus[:] = res.scaled_g * (1 - 3e-3 * rng.uniform(0.9, 1.1, 600))
+        res.scaled_gofr_minus[:] = res.scaled_g * (1 + 3e-3 * rng.uniform(0.9, 1.1, 600))
+        res.save_results(600)
+        paths.append(join(str(tmp_path), f"P12_T300.00_J{job}_data_points.npz"))
+        parts.append(res)
+    loaded = ref_pimc.BoxResultPM()
+    loaded.hash_vib, loaded.hash_rho = Data.hash_vib, Data.hash_rho
+    loaded.load_multiple_results(paths)
+    assert loaded.samples == 1200
+    for name in ("scaled_rho", "scaled_g", "scaled_gofr_plus", "scaled_gofr_minus"):
+        assert np.array_equal(getattr(loaded, name), np.concatenate([getattr(p, name) for p in parts]))
+    got = ref_stats.basic_jackknife_analysis(300.0, loaded, {"E": 0.01, "Cv": 2e-5})
+    want = stats_oracle.basic_jackknife_analysis(300.0, loaded.scaled_rho, loaded.scaled_g, loaded.scaled_gofr_plus,
+                                                 loaded.scaled_gofr_minus, 0.01, 2e-5)
+    for key, value in want.items():
+        assert np.isclose(got[key], value, rtol=1e-10, atol=1e-14), key
+    # and the other way round: a file written by the reference loads here
+    theirs = ref_pimc.BoxResultPM(data=Data)
+    theirs.path_root, theirs.id_job = str(tmp_path), 7
+    for name in ("scaled_rho", "scaled_g", "scaled_gofr_plus", "scaled_gofr_minus"):
+        getattr(theirs, name)[:] = getattr(parts[0], name)
+    theirs.save_results(600)
+    back = pimc.BoxResultPM()
+    back.load_multiple_results([join(str(tmp_path), "P12_T300.00_J7_data_points.npz")])
+    assert back.samples == 600 and np.array_equal(back.scaled_gofr_minus, parts[0].scaled_gofr_minus)
