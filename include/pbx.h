@@ -61,7 +61,8 @@ enum {
                                        /* min(A, A_rho) sampling surfaces (bit-parity runs with A_rho > A) */
     PBX_FLAG_M_TAU_PM       = 1u << 2, /* g+/- use exp(-tau+/- V), the consistent beta +/- delta_beta      */
                                        /* estimator; off = the reference's exp(-tau V) for all three       */
-                                       /* (pimc.py:1183).  Needs PBX_FLAG_PM and a register-resident shape. */
+                                       /* (pimc.py:1183).  Needs PBX_FLAG_PM, a register-resident shape and */
+                                       /* a library built with PBX_WITH_MTAU=1 (not the default build).     */
     PBX_FLAG_EIG_JACOBI     = 1u << 3, /* M = U exp(-tau lambda) U^T by a Jacobi eigensolve (reference's  */
                                        /* formulation); default is a scaling-and-squaring exp(-tau V)      */
     PBX_FLAG_FORCE_GENERIC  = 1u << 4, /* never use the register-resident small-A kernels                 */
@@ -105,6 +106,9 @@ typedef struct pbx_rho {
 typedef struct pbx_plan pbx_plan;   /* opaque */
 
 int pbx_abi_version(void);
+/* optional parts compiled into this library: PBX_FEATURE_MTAU = the PBX_FLAG_M_TAU_PM kernels (build with PBX_WITH_MTAU=1) */
+enum { PBX_FEATURE_MTAU = 1 };
+int pbx_library_features(void);
 const char *pbx_last_error(void);
 /* number of CUDA devices visible (0 if none / driver missing) */
 int pbx_device_count(void);
@@ -116,6 +120,12 @@ int pbx_device_count(void);
 int pbx_plan_create(const pbx_model *vib, const pbx_rho *rho, int32_t beads, double beta,
                     double delta_beta, uint32_t flags, int32_t device, pbx_plan **out);
 int pbx_plan_destroy(pbx_plan *plan);
+
+/* Register-resident kernels exist for the shapes compiled into the library (csrc/shapes.def).  Further shapes can be
+ * compiled at run time into their own shared library (pibronic_b200/jit.py runs nvcc on csrc/pbx_fast_inst.cu) and
+ * registered here; plans created afterwards use them.  pbx_has_register_kernel: 1 if (A, N, A_rho) is known. */
+int pbx_has_register_kernel(int32_t A, int32_t N, int32_t A_rho);
+int pbx_register_shape_library(const char *path);
 
 /* Introspection of the precomputed host tables (tests compare them with the reference's).
  * name is one of: "d_vib"[A][N] "d_rho"[Ar][N] "delta_vib"[A] "delta_rho"[Ar] "weights"[Ar]

@@ -65,11 +65,14 @@ def lib():
     vp, i32, i64, u32, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
     sigs = {
         "pbx_abi_version": (C.c_int, []),
+        "pbx_library_features": (C.c_int, []),
         "pbx_last_error": (C.c_char_p, []),
         "pbx_device_count": (C.c_int, []),
         "pbx_plan_create": (C.c_int, [C.POINTER(PbxModel), C.POINTER(PbxRho), i32, dbl, dbl, u32, i32, C.POINTER(vp)]),
         "pbx_plan_destroy": (C.c_int, [vp]),
         "pbx_plan_table": (i64, [vp, C.c_char_p, _dp, i64]),
+        "pbx_has_register_kernel": (C.c_int, [i32, i32, i32]),
+        "pbx_register_shape_library": (C.c_int, [C.c_char_p]),
         "pbx_plan_is_fast": (C.c_int, [vp]),
         "pbx_plan_kernel_path": (C.c_int, [vp]),
         "pbx_plan_launch_count": (i64, [vp]),
@@ -98,8 +101,8 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ("pbx_abi_version", "pbx_last_error", "pbx_device_count", "pbx_plan_create", "pbx_plan_destroy",
-                    "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_kernel_path", "pbx_plan_launch_count", "pbx_plan_launch_param_bytes", "pbx_sample_eval_dev",
+EXPORTED_SYMBOLS = ("pbx_abi_version", "pbx_library_features", "pbx_last_error", "pbx_device_count", "pbx_plan_create", "pbx_plan_destroy",
+                    "pbx_has_register_kernel", "pbx_register_shape_library", "pbx_plan_table", "pbx_plan_is_fast", "pbx_plan_kernel_path", "pbx_plan_launch_count", "pbx_plan_launch_param_bytes", "pbx_sample_eval_dev",
                     "pbx_sample_eval_host", "pbx_eval_coords_dev", "pbx_eval_coords_host", "pbx_sample_coords_dev",
                     "pbx_eval_stages_dev", "pbx_chain_trace_dev", "pbx_block_sums_dev", "pbx_stats_dev", "pbx_stats_host",
                     "pbx_stats_last", "pbx_stats_arrays_dev", "pbx_stats_arrays_host", "pbx_math_probe_dev", "pbx_fp64_peak_tflops", "pbx_fp64_peak_tflops_kind")
@@ -139,7 +142,9 @@ class Plan:
     """One (model, rho, beads, beta) evaluation plan on one GPU: owns the device constant tables."""
 
     def __init__(self, energy, omega, linear, quadratic, rho_energy, rho_omega, rho_linear, beads, beta,
-                 delta_beta, flags=FLAG_PM, device=0):
+                 delta_beta, flags=FLAG_PM, device=0, jit=None):
+        """jit=True (or PBX_JIT=1 in the environment): a shape without a compiled register-resident kernel gets one
+        built with nvcc on first use (pibronic_b200/jit.py; cached next to the package), if it is small enough"""
         L = lib()
         self._handle = None
         energy, omega = _f64(energy), _f64(omega)
@@ -156,6 +161,9 @@ class Plan:
         rho_linear = None if rho_linear is None else _f64(rho_linear)
         if rho_linear is not None:
             assert rho_linear.shape == (rho_omega.shape[0], Ar)
+        if (os.environ.get("PBX_JIT", "0") == "1") if jit is None else jit:
+            from . import jit as _jit
+            _jit.ensure_shape(A, N, Ar)
         vib = PbxModel(A, N, _ptr(energy), _ptr(omega), _ptr(linear), _ptr(quadratic))
         rho = PbxRho(Ar, rho_omega.shape[0], _ptr(rho_energy), _ptr(rho_omega), _ptr(rho_linear))
         handle = C.c_void_p()
@@ -304,6 +312,13 @@ def stats_arrays_dev(out4, beta, delta_beta, stream=None):
     _check(lib().pbx_stats_arrays_dev(_devptr(out4), int(out4.shape[1]), float(beta), float(delta_beta),
                                       int(out4.device.index or 0), values, _stream_handle(stream)))
     return dict(zip(STAT_NAMES, (float(v) for v in values)))
+
+
+FEATURE_MTAU = 1
+
+
+def has_feature(bit):
+    return bool(lib().pbx_library_features() & bit)
 
 
 def device_count():

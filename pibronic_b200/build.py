@@ -23,7 +23,9 @@ OBJ_DIR = join(ROOT, "build", "pbx" + (("_" + _VARIANT) if _VARIANT else ""))
 
 NVCC = os.environ.get("NVCC", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# PBX_WITH_MTAU=1: also build the PBX_FLAG_M_TAU_PM kernels (consistent estimator, not part of the reference's path)
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + \
+    (["-DPBX_WITH_MTAU=1"] if os.environ.get("PBX_WITH_MTAU") == "1" else []) + \
     os.environ.get("PBX_EXTRA_NVCC_FLAGS", "").split()
 
 
@@ -76,7 +78,7 @@ def build(force=False, verbose=False):
         logs = list(pool.map(lambda job: _run(job[1]), jobs))
     if verbose:
         print("\n".join(logs))
-    _run([NVCC, *ARCH, "-shared", "-o", OUT, *[obj for obj, _ in jobs], "-cudart", "static"])
+    _run([NVCC, *ARCH, "-shared", "-o", OUT, *[obj for obj, _ in jobs], "-cudart", "static", "-ldl"])
     with open(stamp, "w") as fh:
         fh.write(digest)
     return OUT

@@ -1,4 +1,6 @@
 // C ABI of the pbx library (include/pbx.h): plan management, launch orchestration, reductions.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -485,6 +487,7 @@ long long generic_chunk(const pbx_plan* p, long long n, bool with_coords) {
 extern "C" {
 
 int pbx_abi_version(void) { return PBX_ABI_VERSION; }
+int pbx_library_features(void) { return (PBX_WITH_MTAU ? PBX_FEATURE_MTAU : 0); }
 const char* pbx_last_error(void) { return g_last_error.c_str(); }
 
 int pbx_device_count(void) {
@@ -507,10 +510,12 @@ int pbx_plan_create(const pbx_model* vib, const pbx_rho* rho, int32_t beads, dou
     const bool want_fast = !(flags & PBX_FLAG_FORCE_GENERIC) && p->scale;
     if (want_fast) p->fast = find_fast_kernel(p->H.A, p->H.N, p->H.Ar);
     p->mtau = flags & PBX_FLAG_M_TAU_PM;
+    // a run-time compiled shape carries the default variants only
+    if (p->fast && ((p->jacobi && !(p->fast->caps & FAST_CAP_JACOBI)) || (p->mtau && !(p->fast->caps & FAST_CAP_MTAU)))) p->fast = nullptr;
     if (p->mtau && (!p->pm || p->jacobi || !p->fast)) {
         delete p;
-        return fail(PBX_ERR_UNSUPPORTED, "PBX_FLAG_M_TAU_PM needs PBX_FLAG_PM, the default exp(-tau V) builder and a model shape "
-                                         "with a register-resident kernel (csrc/shapes.def)");
+        return fail(PBX_ERR_UNSUPPORTED, "PBX_FLAG_M_TAU_PM needs PBX_FLAG_PM, the default exp(-tau V) builder, a model shape "
+                                         "with a register-resident kernel (csrc/shapes.def) and a library built with PBX_WITH_MTAU=1");
     }
     if (p->fast) {
         p->fast_tables.assign(p->fast->table_bytes, 0);
@@ -593,6 +598,21 @@ int64_t pbx_plan_table(const pbx_plan* p, const char* name, double* out, int64_t
     const int64_t avail = (int64_t)v->size();
     if (out && count > 0) std::memcpy(out, v->data(), (size_t)std::min(count, avail) * sizeof(double));
     return avail;
+}
+
+int pbx_has_register_kernel(int32_t A, int32_t N, int32_t A_rho) { return find_fast_kernel(A, N, A_rho) ? 1 : 0; }
+
+int pbx_register_shape_library(const char* path) {
+    if (!path) return fail(PBX_ERR_ARG, "null path");
+    void* handle = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!handle) return fail(PBX_ERR_ARG, std::string("dlopen failed: ") + dlerror());
+    typedef const FastKernelEntry* (*entry_fn)(void);
+    entry_fn fn = (entry_fn)dlsym(handle, "pbx_jit_entry");
+    if (!fn) { dlclose(handle); return fail(PBX_ERR_ARG, "pbx_jit_entry not found in the library"); }
+    const FastKernelEntry* e = fn();
+    if (!e || e->A < 1 || e->N < 1 || e->AR < 1) { dlclose(handle); return fail(PBX_ERR_ARG, "bad kernel entry"); }
+    register_fast_kernel(e);       // already known: keep the first one (the handle stays open either way)
+    return PBX_OK;
 }
 
 int pbx_plan_is_fast(const pbx_plan* p) { return (p && p->fast) ? 1 : 0; }

@@ -35,6 +35,12 @@
 #ifndef PBX_UNROLL_H
 #define PBX_UNROLL_H 1       // 1: unroll the normal-pair loop of the sampler phase (independent chains interleave)
 #endif
+#ifndef PBX_WITH_MTAU
+#define PBX_WITH_MTAU 0      // 1: also instantiate the PBX_FLAG_M_TAU_PM kernels (consistent estimator; not in the reference)
+#endif
+#ifndef PBX_WITH_JACOBI
+#define PBX_WITH_JACOBI 1    // 0: no Jacobi-eigensolve variants (run-time compiled shapes, pibronic_b200/jit.py)
+#endif
 #ifndef PBX_DELTA_EXP
 #define PBX_DELTA_EXP 1      // 1: O(tau+-) = O(tau) * exp(delta), delta from analytic difference tables
 #endif
@@ -444,8 +450,11 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
 }
 
 // type-erased launcher stored in the plan
+enum { FAST_CAP_JACOBI = 1, FAST_CAP_MTAU = 2 };
+
 struct FastKernelEntry {
     int A, N, AR;
+    int caps;                // FAST_CAP_*: which optional variants this build carries
     size_t table_bytes;
     void (*fill)(const HostTables&, void* dst);
     cudaError_t (*launch)(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share, bool mtau,
@@ -503,18 +512,32 @@ template <int A, int N, int AR>
 cudaError_t launch_fast(const void* tables, const FastLaunch& L, int mode, bool pm, bool jacobi, bool share, bool mtau,
                         cudaStream_t stream) {
     const auto& T = *reinterpret_cast<const FastTables<A, N, AR>*>(tables);
+#if PBX_WITH_MTAU
+#define PBX_DISPATCH_MTAU(MODE_) if (pm && mtau) return launch_share<A, N, AR, MODE_, true, false, true>(T, L, share, stream);
+#else
+#define PBX_DISPATCH_MTAU(MODE_) if (mtau) return cudaErrorNotSupported;
+#endif
+#if PBX_WITH_JACOBI
+#define PBX_DISPATCH_JACOBI(MODE_)                                                                                       \
+    if (jacobi) return pm ? launch_share<A, N, AR, MODE_, true, true>(T, L, share, stream)                              \
+                          : launch_share<A, N, AR, MODE_, false, true>(T, L, share, stream);
+#else
+#define PBX_DISPATCH_JACOBI(MODE_) if (jacobi) return cudaErrorNotSupported;
+#endif
 #define PBX_DISPATCH(MODE_)                                                                               \
-    if (pm && mtau) return launch_share<A, N, AR, MODE_, true, false, true>(T, L, share, stream);        \
-    if (pm) return jacobi ? launch_share<A, N, AR, MODE_, true, true>(T, L, share, stream)               \
-                          : launch_share<A, N, AR, MODE_, true, false>(T, L, share, stream);             \
-    return jacobi ? launch_share<A, N, AR, MODE_, false, true>(T, L, share, stream)                      \
-                  : launch_share<A, N, AR, MODE_, false, false>(T, L, share, stream);
+    PBX_DISPATCH_MTAU(MODE_)                                                                              \
+    PBX_DISPATCH_JACOBI(MODE_)                                                                            \
+    if (pm) return launch_share<A, N, AR, MODE_, true, false>(T, L, share, stream);                      \
+    return launch_share<A, N, AR, MODE_, false, false>(T, L, share, stream);
     if (mode == MODE_SAMPLE) { PBX_DISPATCH(MODE_SAMPLE) }
     PBX_DISPATCH(MODE_COORDS)
 #undef PBX_DISPATCH
+#undef PBX_DISPATCH_MTAU
+#undef PBX_DISPATCH_JACOBI
 }
 
-// defined in pbx_fast_registry.cu
+// defined in pbx_fast_registry.cu: shapes compiled into the library, then shapes registered at run time
 const FastKernelEntry* find_fast_kernel(int A, int N, int AR);
+bool register_fast_kernel(const FastKernelEntry* entry);
 
 }  // namespace pbx

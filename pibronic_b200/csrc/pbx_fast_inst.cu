@@ -8,3 +8,8 @@ namespace pbx {
 #define PBX_CAT(a, b, c, d) PBX_CAT_(a, b, c, d)
 extern const FastKernelEntry PBX_CAT(fast_entry_, PBX_A, PBX_N, PBX_AR) = make_entry<PBX_A, PBX_N, PBX_AR>();
 }  // namespace pbx
+
+#ifdef PBX_JIT_LIBRARY
+// a shape compiled at run time into its own shared library (pibronic_b200/jit.py), loaded with pbx_register_shape_library
+extern "C" const pbx::FastKernelEntry* pbx_jit_entry(void) { return &pbx::PBX_CAT(fast_entry_, PBX_A, PBX_N, PBX_AR); }
+#endif

@@ -270,7 +270,7 @@ cudaError_t launch_ws_one(const FastTables<A, N, AR>& T, const FastLaunch& L_in,
     kernel<<<(unsigned)blocks, WS_THREADS, smem, stream>>>(T, L);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (PM && (PBX_DELTA_EXP || MTAU))   // recompute the (normally zero) flagged samples with full exponentials
+    if constexpr (PM && (PBX_DELTA_EXP || MTAU))   // recompute the (normally zero) flagged samples with full exponentials
         return launch_one<A, N, AR, MODE_REDO, PM, false, SHARE, MTAU>(T, L, stream);
     return cudaSuccess;
 }
@@ -284,19 +284,26 @@ cudaError_t launch_fast_ws(const void* tables, const FastLaunch& L, bool pm, boo
     if constexpr (ws_smem_bytes<N>() > 227 * 1024)      // ring does not fit an SM: one-role kernel
         return launch_fast<A, N, AR>(tables, L, MODE_SAMPLE, pm, false, share, mtau, stream);
     const auto& T = *reinterpret_cast<const FastTables<A, N, AR>*>(tables);
+#if !PBX_WITH_MTAU
+    if (mtau) return cudaErrorNotSupported;
+#endif
     if constexpr (A == AR) {
         if (share) {
+#if PBX_WITH_MTAU
             if (pm && mtau) return launch_ws_one<A, N, AR, true, true, true>(T, L, stream);
+#endif
             return pm ? launch_ws_one<A, N, AR, true, true>(T, L, stream) : launch_ws_one<A, N, AR, false, true>(T, L, stream);
         }
     }
+#if PBX_WITH_MTAU
     if (pm && mtau) return launch_ws_one<A, N, AR, true, false, true>(T, L, stream);
+#endif
     return pm ? launch_ws_one<A, N, AR, true, false>(T, L, stream) : launch_ws_one<A, N, AR, false, false>(T, L, stream);
 }
 
 template <int A, int N, int AR>
 constexpr FastKernelEntry make_entry() {
-    return FastKernelEntry{A, N, AR, sizeof(FastTables<A, N, AR>), &fill_fast_tables<A, N, AR>, &launch_fast<A, N, AR>,
+    return FastKernelEntry{A, N, AR, (PBX_WITH_JACOBI ? FAST_CAP_JACOBI : 0) | (PBX_WITH_MTAU ? FAST_CAP_MTAU : 0), sizeof(FastTables<A, N, AR>), &fill_fast_tables<A, N, AR>, &launch_fast<A, N, AR>,
                            &launch_fast_ws<A, N, AR>, &ws_launches<N>};
 }
 

@@ -743,6 +743,41 @@ def test_simple_and_plus_minus_wrappers(cuda, tmp_path):
     assert loaded.samples == 100 and np.array_equal(loaded.scaled_gofr_plus, res.scaled_gofr_plus)
 
 
+def test_run_time_compiled_shape_uses_the_register_resident_kernel(cuda):
+    """a (5, 3, 5) model is not in csrc/shapes.def: by default it runs on the fused tensor-core kernel; with jit=True
+    pibronic_b200.jit compiles pbx_fast_inst.cu for the shape (nvcc, cached under pibronic_b200/_jit/), registers it and the
+    plan runs the warp-specialised register-resident kernel.  Both against the oracle, and against each other."""
+    import shutil
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import jit, synthetic
+    from pibronic_b200.model_io import VMK
+    if shutil.which("nvcc") is None:
+        pytest.skip("no nvcc on this box")
+    model = synthetic.coupled_model(5, 3, (0.05, 0.2), (1.0, 1.4), seed=535, quadratic=0.08)
+    rho = synthetic.diagonal_of(model)
+    P, T = 24, 300.0
+    args = (model[VMK.E], model[VMK.w], model[VMK.G1], model[VMK.G2], rho[VMK.E], rho[VMK.w], rho[VMK.G1], P, orc.beta_of(T), orc.DELTA_BETA)
+    default = _cabi.Plan(*args, flags=_cabi.FLAG_PM, device=0)
+    assert default.kernel_path == _cabi.PATH_FUSED_DMMA
+    assert jit.eligible(5, 3, 5) and not jit.eligible(7, 12, 7)
+    compiled = _cabi.Plan(*args, flags=_cabi.FLAG_PM, device=0, jit=True)
+    assert compiled.kernel_path == _cabi.PATH_REGISTER and compiled.is_fast
+    vib_d = dict(A=5, N=3, E=model[VMK.E], w=model[VMK.w], L=model[VMK.G1], Q=model[VMK.G2])
+    rho_d = dict(A=5, N=3, E=rho[VMK.E], w=rho[VMK.w], L=rho[VMK.G1])
+    tab = orc.precompute(vib_d, rho_d, P, T)
+    n = 700
+    a, b = default.sample_eval_host(3, 50, n), compiled.sample_eval_host(3, 50, n)
+    R, _ = drawn_coords(cuda, compiled, 3, 50, n)
+    want = oracle_eval(tab, R)
+    assert rel_err(a, want) < RTOL and rel_err(b, want) < RTOL
+    assert rel_err(compiled.eval_coords_host(R), want) < RTOL
+    # the Jacobi cross-check variant is not part of a run-time compiled shape: such a plan falls back to the blocked kernels
+    jac = _cabi.Plan(*args, flags=_cabi.FLAG_PM | _cabi.FLAG_EIG_JACOBI, device=0)
+    assert not jac.is_fast and rel_err(jac.eval_coords_host(R), want) < RTOL
+    for plan in (default, compiled, jac):
+        plan.close()
+
+
 def test_device_math(cuda):
     """the branch-free log / sqrt / exp / sincos of pbx_device.cuh against numpy, in units of ulp"""
     rng = np.random.default_rng(0)
@@ -794,6 +829,11 @@ def test_large_delta_beta_takes_the_safe_path(cuda, delta_beta):
 
 
 # ------------------------------------------------------------------ the consistent estimator (PBX_FLAG_M_TAU_PM)
+# not part of the reference's path: compiled only with PBX_WITH_MTAU=1 (python -m pibronic_b200.build), skipped otherwise
+needs_mtau = pytest.mark.skipif(not _cabi.has_feature(_cabi.FEATURE_MTAU), reason="library built without PBX_WITH_MTAU=1")
+
+
+@needs_mtau
 def test_consistent_estimator_matches_oracle(cuda, case):
     """g+- with exp(-tau+- V) -- not the reference's estimator (it keeps exp(-tau V), pimc.py:1183) -- against the oracle
     with the same option, on the reference's coordinates and through the fused call; rho and g do not change"""
@@ -823,6 +863,7 @@ def test_consistent_estimator_matches_oracle(cuda, case):
         p.close()
 
 
+@needs_mtau
 def test_consistent_estimator_with_a_large_delta_beta(cuda):
     """delta_beta so large that exp(+-kappa X) is no small correction: the flagged samples take the full-exponential path"""
     from conftest import GoldenCase
@@ -841,6 +882,7 @@ def test_consistent_estimator_with_a_large_delta_beta(cuda):
         plan.close()
 
 
+@needs_mtau
 def test_pimc_reproduces_the_sum_over_states_thermodynamics(cuda):
     """End to end against EXACT numbers: the reference's test model data_set_1 sampled from its rho_1, 2e7 samples of 64
     beads (40 ms), vs the sum-over-states Z, E, Cv its Julia dependency computed (tests/golden/sos/).

@@ -14,13 +14,14 @@ import numpy as np
 from conftest import GoldenCase
 from pibronic_b200 import _cabi
 
-for name, n in (("c2_4x6", 600), ("quad_3x4", 300), ("jt_rho4", 300), ("c4mini_12x24", 40)):
+for name, n in (("c2_4x6", 600), ("quad_3x4", 300), ("jt_rho4", 300), ("c4mini_12x24", 40), ("syn_7x12", 70)):
     case = GoldenCase(name)
-    for extra in (0, _cabi.FLAG_NO_WARPSPEC, _cabi.FLAG_FORCE_GENERIC, _cabi.FLAG_M_TAU_PM):
+    for extra in (0, _cabi.FLAG_NO_WARPSPEC, _cabi.FLAG_FORCE_GENERIC, _cabi.FLAG_M_TAU_PM, _cabi.FLAG_PREFER_DMMA,
+                  _cabi.FLAG_NO_FUSED_DMMA):
         try:
             plan = case.plan(_cabi.FLAG_PM | _cabi.QUIRK_RHO_TRUNC | extra)
         except _cabi.PbxError:
-            continue                      # M_TAU_PM on a shape without a register-resident kernel
+            continue                      # M_TAU_PM without a register-resident kernel / a library built without it
         out, sums = plan.sample_eval_host(7, 5, n, block_size=100)
         got = plan.eval_coords_host(case.R)
         assert np.all(np.isfinite(out)) and np.all(np.isfinite(got))
