@@ -167,6 +167,21 @@ __device__ __forceinline__ void sym_mul(const double (&X)[A * (A + 1) / 2], cons
         }
 }
 
+// C = X*Y + Z for commuting symmetric X, Y and symmetric Z: the leading product of every entry becomes an FMA
+template <int A>
+__device__ __forceinline__ void sym_mul_add(const double (&X)[A * (A + 1) / 2], const double (&Y)[A * (A + 1) / 2],
+                                            const double (&Z)[A * (A + 1) / 2], double (&C)[A * (A + 1) / 2]) {
+#pragma unroll
+    for (int i = 0; i < A; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double acc = Z[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < A; ++k) acc = fma(X[sym(i, k)], Y[sym(k, j)], acc);
+            C[tri(i, j)] = acc;
+        }
+}
+
 // Number of squarings s for exp(X) = (T12(X / 2^s))^(2^s): the smallest s >= 0 with ||X||_1 / 2^s < theta.
 // theta = 1/3 bounds the truncation error of the degree-12 Taylor polynomial by
 // theta^13/13! * e^theta = 1.4e-16 (in the 2-norm, which the 1-norm overestimates), i.e. half an ulp of the O(1) entries of M;
@@ -219,16 +234,17 @@ __device__ __forceinline__ void sym_expm(double (&X)[A * (A + 1) / 2], double (&
 #pragma unroll
     for (int k = 0; k < AA; ++k) W[k] = fma(t12::c1, X3[k], fma(t12::c2, X2[k], t12::c3 * X[k]));
     sym_mul<A>(X3, W, Y0);
+    // every sum as a chain of FMAs (a lone DMUL or DADD costs the FP64 pipe a full slot)
+    double Z[AA];
 #pragma unroll
     for (int k = 0; k < AA; ++k) {
-        W[k] = Y0[k] + fma(t12::c4, X3[k], fma(t12::c5, X2[k], t12::c6 * X[k]));
-        Bm[k] = Y0[k] + fma(t12::c7, X3[k], t12::c8 * X2[k]);
+        W[k] = fma(t12::c4, X3[k], fma(t12::c5, X2[k], fma(t12::c6, X[k], Y0[k])));
+        Bm[k] = fma(t12::c7, X3[k], fma(t12::c8, X2[k], Y0[k]));
+        Z[k] = fma(t12::c9, Y0[k], fma(t12::c10, X3[k], fma(0.5, X2[k], X[k])));
     }
-    sym_mul<A>(W, Bm, M);
 #pragma unroll
-    for (int k = 0; k < AA; ++k) M[k] += fma(t12::c9, Y0[k], fma(t12::c10, X3[k], fma(0.5, X2[k], X[k])));
-#pragma unroll
-    for (int i = 0; i < A; ++i) M[tri(i, i)] += 1.0;
+    for (int i = 0; i < A; ++i) Z[tri(i, i)] += 1.0;
+    sym_mul_add<A>(W, Bm, Z, M);
     for (int q = 0; q < s; ++q) {
         sym_mul<A>(M, M, W);
 #pragma unroll

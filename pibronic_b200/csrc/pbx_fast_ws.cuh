@@ -40,6 +40,9 @@
 #ifndef PBX_WS_REG_CONS
 #define PBX_WS_REG_CONS 224
 #endif
+#ifndef PBX_WS_PARK_NS
+#define PBX_WS_PARK_NS 400   // sleep of a waiting producer between two polls of its "empty" barrier, ns
+#endif
 #ifndef PBX_WS_YP_SMEM
 #define PBX_WS_YP_SMEM 0     // 1: previous bead (recurrence state) in shared memory instead of registers
 #endif
@@ -65,6 +68,20 @@ __device__ __forceinline__ void ws_mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(ws_smem_u32(bar)) : "memory");
+}
+// producer side: between two polls the warp sleeps, so that idle producers (they run ahead of the consumers) do not
+// take issue slots from the consumer warps of their scheduler (ncu counted 1e9 try_wait instructions per launch)
+__device__ __forceinline__ void ws_mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WSP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra WSP_DONE;\n"
+        "nanosleep.u32 %3;\n"
+        "bra WSP_WAIT;\n"
+        "WSP_DONE:\n"
+        "}\n" ::"r"(ws_smem_u32(bar)), "r"(parity), "r"(PBX_WS_PARK_NS), "r"(PBX_WS_PARK_NS) : "memory");
 }
 __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -129,7 +146,7 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
         }
         for (int k = 0; k < n_stage; ++k) {
             const int s = k % WS_STAGES;
-            if (k >= WS_STAGES) ws_mbar_wait(empty_bar(g, s), (uint32_t)((k / WS_STAGES - 1) & 1));
+            if (k >= WS_STAGES) ws_mbar_wait_parked(empty_bar(g, s), (uint32_t)((k / WS_STAGES - 1) & 1));
             double* st = ring + (size_t)s * WS_TB * N * WS_CONS;
 #pragma unroll 1
             for (int jj = 0; jj < WS_TB; ++jj) {
