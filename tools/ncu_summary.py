@@ -13,6 +13,8 @@ KEEP = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__occup
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__inst_executed.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_hit_rate.pct',
+        'l1tex__throughput.avg.pct_of_peak_sustained_active', 'lts__t_sectors.sum',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active',
