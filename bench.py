@@ -137,14 +137,17 @@ def reference_available():
     return ref_runner.available()
 
 
-def cpu_rate(kind, procs, X=CPU_SAMPLES_PER_PROC, B=CPU_BLOCK, seed=0):
+def cpu_rate(kind, procs, X=CPU_SAMPLES_PER_PROC, B=CPU_BLOCK, seed=0, pool=None):
     """aggregate samples*beads/s of `procs` independent shards of the CPU path (kind "reference" or "port"); the
     elapsed time is the slowest shard's block-loop time (setup excluded, like the GPU arm)"""
     import multiprocessing as mp
     worker = _reference_worker if kind == "reference" else _port_worker
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        res = pool.map(worker, [(X, B, seed + 1000 * i) for i in range(procs)])
+    jobs = [(X, B, seed + 1000 * i) for i in range(procs)]
+    if pool is not None:
+        res = pool.map(worker, jobs, chunksize=1)
+    else:
+        with mp.get_context("spawn").Pool(procs) as own:
+            res = own.map(worker, jobs, chunksize=1)
     slowest = max(r[0] for r in res)
     return procs * X * P / slowest, slowest, float(np.mean([r[1] for r in res]))
 
@@ -158,13 +161,15 @@ def run_reference(args, rank):
             else "numpy port of block_compute_pm (oracle/pimc_oracle.py; the staged reference is absent)")
     sample = (f"{procs} processes x {CPU_SAMPLES_PER_PROC} samples (blocks of {CPU_BLOCK}) of the same workload per step; "
               f"{what}, 1 BLAS thread per process")
-    for _ in range(args.warmup):
-        cpu_rate(kind, procs, X=200, B=100)
+    import multiprocessing as mp
     times, rates = [], []
-    for k in range(args.steps):
-        rate, dt, _ = cpu_rate(kind, procs, seed=k)
-        times.append(dt)
-        rates.append(rate)
+    with mp.get_context("spawn").Pool(procs) as pool:      # one pool for the whole run: the imports happen once per worker
+        for _ in range(args.warmup):
+            cpu_rate(kind, procs, X=200, B=100, pool=pool)
+        for k in range(args.steps):
+            rate, dt, _ = cpu_rate(kind, procs, seed=k, pool=pool)
+            times.append(dt)
+            rates.append(rate)
     value = float(np.mean(rates))
     line = {
         "impl": "reference", "metric": "PIMC samples*beads/sec", "value": value, "unit": "samples*beads/s",

@@ -292,6 +292,8 @@ class BoxData:
     quirk_rho_trunc = False  # reproduce pimc.py:1110-1111 when A_rho > A
     eig_jacobi = False       # M from a Jacobi eigensolve instead of the scaling-and-squaring exponential
     force_generic = False    # never use the register-resident kernels
+    jit = None               # True: compile a register-resident kernel for a shape that has none (pibronic_b200/jit.py: nvcc,
+                             # ~1 min once, cached); None: only if PBX_JIT=1.  Default for such shapes: the fused tensor-core kernel
     m_tau_pm = False         # g+- with exp(-tau+- V) (consistent estimator, stats.consistent_jackknife_analysis); the
                              # reference uses exp(-tau V) for all three (pimc.py:1183)
 
@@ -479,7 +481,7 @@ class BoxData:
             vib, rho = self.vib.raw, self.rho.raw
             self._plans[key] = _cabi.Plan(vib['energy'], vib['omega'], vib['linear'], vib['quadratic'],
                                           rho['energy'], rho['omega'], rho['linear'], self.beads, self.beta,
-                                          self.delta_beta if pm else 0.0, flags=flags, device=device)
+                                          self.delta_beta if pm else 0.0, flags=flags, device=device, jit=self.jit)
         return self._plans[key]
 
     def release(self):

@@ -14,9 +14,9 @@ from pibronic_b200 import _cabi, constants, synthetic
 from pibronic_b200.model_io import VMK
 
 
-def run(name, model, rho, P, X, T=300.0, flags=_cabi.FLAG_PM):
+def run(name, model, rho, P, X, T=300.0, flags=_cabi.FLAG_PM, jit=False):
     plan = _cabi.Plan(model[VMK.E], model[VMK.w], model[VMK.G1], model.get(VMK.G2), rho[VMK.E], rho[VMK.w], rho[VMK.G1],
-                      P, constants.beta(T), constants.delta_beta, flags=flags, device=0)
+                      P, constants.beta(T), constants.delta_beta, flags=flags, device=0, jit=jit)
     out = torch.empty((4, X), dtype=torch.float64, device="cuda")
     plan.sample_eval(1, 0, X, out)
     torch.cuda.synchronize()
@@ -30,8 +30,11 @@ def run(name, model, rho, P, X, T=300.0, flags=_cabi.FLAG_PM):
         best = min(best, e0.elapsed_time(e1))
     o = out.cpu().numpy()
     r = o[1] / o[0]
-    print(f"{name:34s} fast={plan.is_fast!s:5s} X={X:8d} P={P:4d} {best:9.3f} ms  {X * P / best * 1e3:.3e} samples*beads/s   "
-          f"<g/rho> = {r.mean():.5g} +- {r.std() / np.sqrt(X):.2g}")
+    sys.path.insert(0, dirname(dirname(abspath(__file__))))
+    from bench import algorithmic_flops_per_sample
+    tf = algorithmic_flops_per_sample(plan.A, plan.N, P, plan.Ar) * X / (best * 1e-3) / 1e12
+    print(f"{name:38s} path={plan.kernel_path} X={X:8d} P={P:4d} {best:9.3f} ms  {X * P / best * 1e3:.3e} samples*beads/s  "
+          f"{tf:6.2f} TFLOP/s algorithmic   <g/rho> = {r.mean():.5g} +- {r.std() / np.sqrt(X):.2g}")
     plan.close()
 
 
@@ -46,9 +49,19 @@ def main():
     run("c3-like  A=2 N=2 P=128 X=1e6", c3, synthetic.diagonal_of(c3), 128, 1_000_000)
     free = synthetic.coupled_model(4, 6, (0.14, 0.45), (10.3, 10.9), mixing=0.0, quadratic=0.0)
     run("c5       c2 with another rho", c2, synthetic.diagonal_of(free), 64, 1_000_000)
-    run("c2 consistent estimator", c2, synthetic.diagonal_of(c2), 64, 1_000_000, flags=_cabi.FLAG_PM | _cabi.FLAG_M_TAU_PM)
+    if _cabi.has_feature(_cabi.FEATURE_MTAU):
+        run("c2 consistent estimator", c2, synthetic.diagonal_of(c2), 64, 1_000_000, flags=_cabi.FLAG_PM | _cabi.FLAG_M_TAU_PM)
     c4 = synthetic.model_c4()
-    run("c4       A=12 N=24 P=256 X=16384", c4, synthetic.diagonal_of(c4), 256, 16384)
+    run("c4       A=12 N=24 P=256 X=18944", c4, synthetic.diagonal_of(c4), 256, 18944)
+    run("c4       blocked kernels (round 1)", c4, synthetic.diagonal_of(c4), 256, 18944, flags=_cabi.FLAG_PM | _cabi.FLAG_NO_FUSED_DMMA)
+    # shapes that are not in csrc/shapes.def: the shape of the reference's largest example model (model_7x12.json) and a (5,3,5) one
+    m712 = synthetic.coupled_model(7, 12, (0.02, 0.3), (0.5, 1.2), seed=23, quadratic=0.06)
+    run("7x12     fused tensor-core kernel", m712, synthetic.diagonal_of(m712), 64, 200_000)
+    run("7x12     blocked kernels (round 1)", m712, synthetic.diagonal_of(m712), 64, 200_000, flags=_cabi.FLAG_PM | _cabi.FLAG_NO_FUSED_DMMA)
+    m535 = synthetic.coupled_model(5, 3, (0.05, 0.2), (1.0, 1.4), seed=535, quadratic=0.08)
+    run("5x3      fused tensor-core kernel", m535, synthetic.diagonal_of(m535), 64, 1_000_000)
+    run("5x3      blocked kernels (round 1)", m535, synthetic.diagonal_of(m535), 64, 1_000_000, flags=_cabi.FLAG_PM | _cabi.FLAG_NO_FUSED_DMMA)
+    run("5x3      run-time compiled register kernel", m535, synthetic.diagonal_of(m535), 64, 1_000_000, jit=True)
 
 
 if __name__ == "__main__":
