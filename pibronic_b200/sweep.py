@@ -118,7 +118,10 @@ class _Point:
 def run_sweep(FS, input_param_dict=None, analytic=True):
     """evaluates every (temperature, beads) point; returns {(P, T): BoxResultPM} of the points this rank evaluated
     (all of them in a single process)"""
+    import os
     import torch
+    if "LOCAL_RANK" in os.environ and torch.cuda.is_available():     # one process per GPU under torchrun: plans AND collectives
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))         # of this rank live on its own device
     params = copy.deepcopy(DEFAULT_PARAMETERS)
     params.update(input_param_dict or {})
     blocks = setup_blocks(params)
