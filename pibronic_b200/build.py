@@ -24,7 +24,8 @@ OBJ_DIR = join(ROOT, "build", "pbx" + (("_" + _VARIANT) if _VARIANT else ""))
 NVCC = os.environ.get("NVCC", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # PBX_WITH_MTAU=1: also build the PBX_FLAG_M_TAU_PM kernels (consistent estimator, not part of the reference's path)
-CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + \
+# -Xfatbin=-compress-all: the device code of ~300 kernels (with line info) shrinks 3x; cuobjdump / ncu read it as before
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xfatbin=-compress-all"] + \
     (["-DPBX_WITH_MTAU=1"] if os.environ.get("PBX_WITH_MTAU") == "1" else []) + \
     os.environ.get("PBX_EXTRA_NVCC_FLAGS", "").split()
 

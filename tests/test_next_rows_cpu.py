@@ -152,3 +152,27 @@ def test_reference_loader_and_jackknife_consume_files_written_here(tmp_path):
     back = pimc.BoxResultPM()
     back.load_multiple_results([join(str(tmp_path), "P12_T300.00_J7_data_points.npz")])
     assert back.samples == 600 and np.array_equal(back.scaled_gofr_minus, parts[0].scaled_gofr_minus)
+
+
+def test_fast_npz_writer_writes_what_numpy_writes(tmp_path):
+    """pibronic_b200.npz_writer.savez == np.savez member for member (names, dtypes, shapes, values), a valid ZIP, and the
+    numpy fallback for what it does not handle"""
+    import zipfile
+    from pibronic_b200 import npz_writer
+    rng = np.random.RandomState(1)
+    members = dict(hash_vib="a" * 128, hash_rho="b" * 128, number_of_samples=2_000_000, s_rho=rng.rand(2_000_000),
+                   s_g=rng.rand(2_000_000), s_gP=rng.rand(300_000), empty=np.empty(0), scalar=np.float64(2.5),
+                   table=np.arange(12, dtype=np.int32).reshape(3, 4))
+    fast, ref = str(tmp_path / "fast.npz"), str(tmp_path / "ref.npz")
+    npz_writer.savez(fast, **members)
+    np.savez(ref, **members)
+    assert zipfile.ZipFile(fast).testzip() is None
+    with np.load(fast) as a, np.load(ref) as b:
+        assert a.files == b.files
+        for name in b.files:
+            assert a[name].dtype == b[name].dtype and a[name].shape == b[name].shape and np.array_equal(a[name], b[name]), name
+    npz_writer.savez(str(tmp_path / "noext"), x=np.arange(3))                     # numpy appends .npz: so does this
+    assert np.array_equal(np.load(str(tmp_path / "noext.npz"))["x"], np.arange(3))
+    strided = np.arange(10.0)[::2]
+    npz_writer.savez(str(tmp_path / "strided.npz"), x=strided)                    # not C-contiguous: numpy writes it
+    assert np.array_equal(np.load(str(tmp_path / "strided.npz"))["x"], strided)
