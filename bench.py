@@ -367,7 +367,7 @@ def facade_e2e(run, device, reps=3):
     (dt,) = run.max_over_ranks([dt])
     return {"value": run.world * X_PER_GPU * P * reps / dt, "unit": "samples*beads/s", "ms_per_call": 1e3 * dt / reps,
             "call": "pibronic_b200.pimc.block_compute_pm(BoxDataPM, BoxResultPM): plan lookup, fused launch into pinned result "
-                    "arrays, block sums, np.savez of the four arrays (tmpfs)", "npz_bytes": int(npz), "calls": reps}
+                    "arrays, block sums, the four arrays written as the reference's .npz (tmpfs)", "npz_bytes": int(npz), "calls": reps}
 
 
 def run_b200(args, rank, local_rank, world):
