@@ -316,14 +316,14 @@ int upload_dmma_tables(pbx_plan* p) {
         }
         ints[(size_t)4 * KS + k] = v;
     }
-    // BIG_TABLE_COPIES identical copies: the CTAs of the fused kernel walk the table in step, and with a single copy every
-    // SM asks the same L2 slice for the same line at the same time (the queue at that slice showed up as ~150 cycles of
-    // long-scoreboard stall per k-step); CTA b reads copy b % BIG_TABLE_COPIES
+    // two tables: the coefficients as they are (blocked kernels: they also return V) and multiplied by -tau (fused kernel:
+    // its tensor-core contraction yields X = -tau V directly)
     double* dq = nullptr;
-    PBX_CUDA(cudaMalloc((void**)&dq, (size_t)BIG_TABLE_COPIES * q.size() * sizeof(double)));
+    PBX_CUDA(cudaMalloc((void**)&dq, 2 * q.size() * sizeof(double)));
     p->dmma_tables = dq;
-    for (int r = 0; r < BIG_TABLE_COPIES; ++r)
-        PBX_CUDA(cudaMemcpy(dq + (size_t)r * q.size(), q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
+    PBX_CUDA(cudaMemcpy(dq, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
+    for (double& v : q) v *= -H.tau[0];
+    PBX_CUDA(cudaMemcpy(dq + q.size(), q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
     PBX_CUDA(cudaMalloc((void**)&p->dev_int_tables, ints.size() * sizeof(int)));
     PBX_CUDA(cudaMemcpy(p->dev_int_tables, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice));
     p->D.q_dmma = dq; p->D.feat = p->dev_int_tables; p->D.tri_ij = p->dev_int_tables + 4 * KS;
@@ -361,9 +361,9 @@ int upload_big_tables(pbx_plan* p) {
     PBX_CUDA(cudaMemcpy(p->big_tab, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
     B.tab = p->big_tab;
     B.Ar = Ar; B.N = N; B.P = H.P; B.n_rho_eval = H.n_rho_eval; B.KS = p->D.KS; B.neg_tau = -H.tau[0];
-    B.q_copy_stride = (long long)p->D.KS * p->D.NT * 32;
     B.share = H.rho_shares_vib ? 1 : 0;
-    B.wcum = p->D.wcum; B.q_dmma = p->D.q_dmma; B.feat = p->D.feat; B.tri_ij = p->D.tri_ij; B.samp = p->D.samp;
+    B.q_dmma = p->D.q_dmma + (size_t)p->D.KS * p->D.NT * 32;      // the -tau scaled table
+    B.wcum = p->D.wcum; B.feat = p->D.feat; B.tri_ij = p->D.tri_ij; B.samp = p->D.samp;
     return PBX_OK;
 }
 

@@ -45,10 +45,6 @@ namespace pbx {
 constexpr int BIG_G = 16;            // beads per group: two m8 row tiles of the coupling contraction
 constexpr int BIG_RS = BIG_G + 2;    // row stride of the coordinate tile (17 beads: the group and the next one)
 constexpr int BIG_WARPS = PBX_BIG_WARPS, BIG_CH = PBX_BIG_CH, BIG_STAGES = PBX_BIG_STAGES, BIG_COPY_SPLIT = PBX_BIG_COPY_SPLIT;
-#ifndef PBX_BIG_TABLE_COPIES
-#define PBX_BIG_TABLE_COPIES 16
-#endif
-constexpr int BIG_TABLE_COPIES = PBX_BIG_TABLE_COPIES;   // identical copies of the coefficient table at different addresses (L2 slices)
 constexpr int BIG_AMAX = 16, BIG_ARMAX = 32, BIG_NMAX_SAMPLER = 32;
 
 enum { BIG_COORDS = 0, BIG_SAMPLE = 1 };
@@ -63,8 +59,7 @@ struct BigParams {
     int tab_doubles;
     int o_al, o_ga, o_d2v, o_d2r, o_lpref, o_lprho, o_drho;
     const double* wcum;      // [Ar]
-    const double* q_dmma;    // [BIG_TABLE_COPIES][KS][NT][32] coupling coefficients in mma fragment order (DevTables::q_dmma)
-    long long q_copy_stride; // doubles between the copies
+    const double* q_dmma;    // [KS][NT][32] coupling coefficients times -tau in mma fragment order (cf. DevTables::q_dmma)
     const int* feat;         // [4 KS]
     const int* tri_ij;       // [8 NT]
     const double* samp;      // [P][N][3]
@@ -158,6 +153,18 @@ __device__ __forceinline__ void big_prod(const BigOp<AT>& X, const BigOp<AT>& Y,
             for (int nt = 0; nt <= mt; ++nt) dmma_884(C.v[mt][nt][0], C.v[mt][nt][1], X.v[mt][ks], Y.v[nt][ks]);
 }
 
+// C += X * Y, same tiles
+template <int AT>
+__device__ __forceinline__ void big_prod_acc(const BigOp<AT>& X, const BigOp<AT>& Y, BigFrag<AT>& C) {
+    constexpr int MT = MidShape<AT>::MT, KS = MidShape<AT>::KS;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt <= mt; ++nt) dmma_884(C.v[mt][nt][0], C.v[mt][nt][1], X.v[mt][ks], Y.v[nt][ks]);
+}
+
 // operand fragment of a matrix in shared memory (row stride LDM): lane (g, c) holds M[8 t + g][4 ks + c]
 template <int AT>
 __device__ __forceinline__ void big_op_load(const double* __restrict__ buf, BigOp<AT>& O, int g, int c) {
@@ -232,7 +239,7 @@ pbx_big_kernel(const BigParams Q) {
     // the CTA consumes the ring in one sequence of chunks, the same in every warp; slot and phase advance incrementally
     // (no divisions on the critical path: thread 0, the producer, must not fall behind the other warps)
     int chunks_left = (int)(iters * ((Q.P + BIG_G - 1) / BIG_G) * n_chunks);      // chunks this CTA has not consumed yet
-    const double* q_src = Q.q_dmma + (size_t)(blockIdx.x % BIG_TABLE_COPIES) * Q.q_copy_stride;
+    const double* q_src = Q.q_dmma;
     auto issue_chunk = [&](int i, int slot) {      // chunk i of the table -> ring slot (one thread)
         const int k0 = i * BIG_CH;                          // KS is a multiple of BIG_CH (zero padded)
         const uint32_t bytes = (uint32_t)(BIG_CH * NT * 32 * sizeof(double));
@@ -551,7 +558,7 @@ pbx_big_kernel(const BigParams Q) {
                 double fro = 0.0;
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const double x0 = acc[m][j][0] * Q.neg_tau, x1 = acc[m][j][1] * Q.neg_tau;
+                    const double x0 = acc[m][j][0], x1 = acc[m][j][1];          // the table carries the factor -tau
                     *reinterpret_cast<double2*>(Xs + (8 * m + g) * XSTR + 8 * j + 2 * c) = make_double2(x0, x1);
                     const double w0 = ((fro_valid >> (2 * j)) & 1u) ? (((fro_diag >> (2 * j)) & 1u) ? 1.0 : 2.0) : 0.0;
                     const double w1 = ((fro_valid >> (2 * j + 1)) & 1u) ? (((fro_diag >> (2 * j + 1)) & 1u) ? 1.0 : 2.0) : 0.0;
@@ -613,17 +620,29 @@ pbx_big_kernel(const BigParams Q) {
                     const double y = nrm[je] * (double)(PBX_EXPM_THETA_INV * PBX_EXPM_THETA_INV);
                     if (y >= 1.0) s = ((((__double2hiint(y) >> 20) & 0x7ff) - 1023) >> 1) + 1;
                     s = s > 60 ? 60 : s;
-                    const double scale = __hiloint2double((1023 - s) << 20, 0);
 #pragma unroll
                     for (int t = 0; t < MT; ++t)
 #pragma unroll
-                        for (int ks = 0; ks < KSA; ++ks) oX.v[t][ks] = opi[t][ks] >= 0 ? Xp[opi[t][ks]] * scale : 0.0;
+                        for (int ks = 0; ks < KSA; ++ks) oX.v[t][ks] = opi[t][ks] >= 0 ? Xp[opi[t][ks]] : 0.0;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                         for (int nt = 0; nt <= mt; ++nt)
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) x1.v[mt][nt][e] = aci[mt][nt][e] >= 0 ? Xp[aci[mt][nt][e]] * scale : 0.0;
+                            for (int e = 0; e < 2; ++e) x1.v[mt][nt][e] = aci[mt][nt][e] >= 0 ? Xp[aci[mt][nt][e]] : 0.0;
+                    if (s > 0) {          // warp-uniform; no squarings (hence no scaling) on most workloads
+                        const double scale = __hiloint2double((1023 - s) << 20, 0);
+#pragma unroll
+                        for (int t = 0; t < MT; ++t)
+#pragma unroll
+                            for (int ks = 0; ks < KSA; ++ks) oX.v[t][ks] *= scale;
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt <= mt; ++nt)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) x1.v[mt][nt][e] *= scale;
+                    }
                 }
                 if constexpr (CHN) chain_k(0, 1);
                 if constexpr (EXP) {
@@ -647,9 +666,9 @@ pbx_big_kernel(const BigParams Q) {
                     big_op_load<AT>(B1, oA, g, c);
                     big_op_load<AT>(B2, oB, g, c);
                     big_prod<AT>(oA, oB, y0f);
-                    PBX_FRAG_LOOP {
-                        fb.v[mt][nt][e] = y0f.v[mt][nt][e] + fma(t12::c4, x3.v[mt][nt][e], fma(t12::c5, x2.v[mt][nt][e], t12::c6 * x1.v[mt][nt][e]));
-                        fo.v[mt][nt][e] = y0f.v[mt][nt][e] + fma(t12::c7, x3.v[mt][nt][e], t12::c8 * x2.v[mt][nt][e]);
+                    PBX_FRAG_LOOP {      // sums as FMA chains: a lone DMUL or DADD costs the FP64 units a full slot
+                        fb.v[mt][nt][e] = fma(t12::c4, x3.v[mt][nt][e], fma(t12::c5, x2.v[mt][nt][e], fma(t12::c6, x1.v[mt][nt][e], y0f.v[mt][nt][e])));
+                        fo.v[mt][nt][e] = fma(t12::c7, x3.v[mt][nt][e], fma(t12::c8, x2.v[mt][nt][e], y0f.v[mt][nt][e]));
                     }
                 }
                 __syncwarp();                                   // every lane has read B1, B2 and its rows of T
@@ -676,10 +695,11 @@ pbx_big_kernel(const BigParams Q) {
                 if constexpr (EXP) {
                     big_op_load<AT>(B0, oA, g, c);
                     big_op_load<AT>(B1, oB, g, c);
-                    big_prod<AT>(oA, oB, fo);
-                    PBX_FRAG_LOOP fo.v[mt][nt][e] = fo.v[mt][nt][e] +
+                    // the additive terms are the start value of the product's accumulators
+                    PBX_FRAG_LOOP fo.v[mt][nt][e] =
                         fma(t12::c9, y0f.v[mt][nt][e], fma(t12::c10, x3.v[mt][nt][e], fma(0.5, x2.v[mt][nt][e], x1.v[mt][nt][e]))) +
                         (((8 * mt + g) == (8 * nt + 2 * c + e)) ? 1.0 : 0.0);
+                    big_prod_acc<AT>(oA, oB, fo);
                     double* cur = B2;
                     double* nxt = B0;
                     big_frag_store<AT>(cur, fo, g, c);
