@@ -65,18 +65,22 @@ def build(force=False, verbose=False):
     if not force and os.path.isfile(OUT) and os.path.isfile(stamp) and open(stamp).read() == digest:
         return OUT
     jobs = []
+    # PBX_VARIANT_ONLY_FAST=1: a variant build recompiles the register-resident shapes only and links the main build's
+    # other objects (kernel experiments on the small shapes in a minute instead of ten)
+    main_dir = join(ROOT, "build", "pbx")
+    reuse = bool(_VARIANT) and os.environ.get("PBX_VARIANT_ONLY_FAST") == "1"
     for name in ("pbx_api.cu", "pbx_fast_registry.cu"):
-        obj = join(OBJ_DIR, name.replace(".cu", ".o"))
-        jobs.append((obj, [NVCC, *ARCH, *CFLAGS, "-c", join(CSRC, name), "-o", obj]))
+        obj = join(main_dir if reuse else OBJ_DIR, name.replace(".cu", ".o"))
+        jobs.append((obj, None if reuse else [NVCC, *ARCH, *CFLAGS, "-c", join(CSRC, name), "-o", obj]))
     for (A, N, AR) in shapes():
         obj = join(OBJ_DIR, f"pbx_fast_{A}_{N}_{AR}.o")
         jobs.append((obj, [NVCC, *ARCH, *CFLAGS, f"-DPBX_A={A}", f"-DPBX_N={N}", f"-DPBX_AR={AR}",
                            "-c", join(CSRC, "pbx_fast_inst.cu"), "-o", obj]))
     for A in BIG_SURFACES:      # fused large-A kernel, one translation unit per number of surfaces
-        obj = join(OBJ_DIR, f"pbx_big_{A}.o")
-        jobs.append((obj, [NVCC, *ARCH, *CFLAGS, f"-DPBX_BIG_AT={A}", "-c", join(CSRC, "pbx_big_inst.cu"), "-o", obj]))
+        obj = join(main_dir if reuse else OBJ_DIR, f"pbx_big_{A}.o")
+        jobs.append((obj, None if reuse else [NVCC, *ARCH, *CFLAGS, f"-DPBX_BIG_AT={A}", "-c", join(CSRC, "pbx_big_inst.cu"), "-o", obj]))
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
-        logs = list(pool.map(lambda job: _run(job[1]), jobs))
+        logs = list(pool.map(lambda job: _run(job[1]) if job[1] else "", jobs))
     if verbose:
         print("\n".join(logs))
     _run([NVCC, *ARCH, "-shared", "-o", OUT, *[obj for obj, _ in jobs], "-cudart", "static", "-ldl"])

@@ -27,10 +27,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 enum : uint32_t { STREAM_NORMALS = 0u, STREAM_SOURCE = 1u };
 
-// 64 random bits -> double in (0, 1]
+// 64 random bits -> double in (0, 1]: (n + 1) 2^-53 with n the top 53 bits.  n + 1 <= 2^53 converts exactly and the
+// power of two is an integer subtraction on the exponent field (the FP64 pipe is the bottleneck, the integer pipe is not)
 __device__ __forceinline__ double u01_open_low(uint32_t hi, uint32_t lo) {
     const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
-    return ((double)(bits >> 11) + 1.0) * 0x1.0p-53;
+    const double d = (double)((bits >> 11) + 1ull);
+    return __hiloint2double(__double2hiint(d) - (53 << 20), __double2loint(d));
 }
 // 64 random bits -> double in [0, 1)
 __device__ __forceinline__ double u01_half_open(uint32_t hi, uint32_t lo) {
@@ -42,70 +44,71 @@ __device__ __forceinline__ double u01_half_open(uint32_t hi, uint32_t lo) {
 // Branch-free FP64 elementary functions for the argument ranges this path needs.  The CUDA math
 // library versions carry slow-path branches (denormals, huge arguments, special values); a branch
 // ends the basic block, so ptxas cannot interleave independent evaluations -- in the sampler phase
-// that left one dependent chain at a time in flight (profiles/r01_summary.md).  Coefficients sit in
-// __constant__ memory: one LDCU.128 fetches two of them (an FP64 immediate costs two UMOVs).
+// that left one dependent chain at a time in flight (profiles/r01_summary.md).  Every FP64 instruction
+// of the sampler competes with the estimator for the FP64 units, so the functions are table driven
+// (pbx_math_tables.h, 10 KB, L1 resident) with short polynomials: a Box-Muller pair costs 28 FP64
+// instructions (round 1: 47) and 5 conversions.  Coefficients sit in __constant__ memory: one LDCU.128
+// fetches two of them (an FP64 immediate costs two UMOVs).
 // Accuracy of each: a few ulp (checked against numpy in tests/test_gpu_parity.py::test_device_math).
 // ------------------------------------------------------------------------------------------
-static __constant__ double kLog1pC[6] = {-1.0 / 2, 1.0 / 3, -1.0 / 4, 1.0 / 5, -1.0 / 6, 1.0 / 7};   // log1p(t) = t + t^2 Q(t)
+static __constant__ double kNeg2Log1pC[4] = {-2.0, 1.0, -2.0 / 3, 1.0 / 2};   // -2 log1p(t) = t (-2 + t - 2/3 t^2 + t^3/2 - 2/5 t^4)
 static __constant__ double kExpC[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
                                  1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
-static __constant__ double kSinC[8] = {-1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 362880, -1.0 / 39916800, 1.0 / 6227020800.0,
-                                -1.0 / 1307674368000.0, 0.0};
-static __constant__ double kCosC[8] = {-1.0 / 2, 1.0 / 24, -1.0 / 720, 1.0 / 40320, -1.0 / 3628800, 1.0 / 479001600,
-                                -1.0 / 87178291200.0, 1.0 / 20922789888000.0};
 constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
 
 // single MUFU instruction (the rounded intrinsic rsqrtf carries a slow-path branch)
 __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// ln(u) for a normal, positive, finite u (here u in [2^-53, 1]): u = 2^k m with m in [0.75, 1.5),
-// ln m = -ln(rc) + log1p(m rc - 1) with rc ~ 1/m from a 97-entry table (pbx_math_tables.h; the pair of u's
-// lane is one 16-byte L1 load), |m rc - 1| <= 1/192 so a degree-7 series is exact to 7e-20.  The centre of
-// the cell around m = 1 is exactly 1: ln u keeps full RELATIVE accuracy for u -> 1.  11 FP64 instructions.
-__device__ __forceinline__ double log_pos(double u) {
+// -2 ln(u) for a normal, positive u in [2^-63, 1]: u = 2^k m with m in [0.75, 1.5),
+// -2 ln u = -2 k ln 2 + 2 ln(rc) - 2 log1p(m rc - 1) with rc ~ 1/m from a 385-entry table (the pair of u's lane is one
+// 16-byte L1 load) and -2 k ln 2 from a second one; |m rc - 1| <= 1/768, so the series ends at t^5 (remainder 1e-18).
+// The centre of the cell around m = 1 is exactly 1 and both table terms vanish there: the result keeps its RELATIVE
+// accuracy for u -> 1 (6e-16 at the edge of that cell).  7 FP64 instructions.
+__device__ __forceinline__ double neg2_log_pos(double u) {
     const int hi = __double2hiint(u), lo = __double2loint(u);
     const int frac = hi & 0x000fffff;
     const bool big = frac >= 0x00080000;                       // mantissa >= 1.5: use m / 2 in [0.75, 1)
-    const int k = (hi >> 20) - 1023 + (big ? 1 : 0);
-    const int idx = big ? ((frac + 0x2000) >> 14) - 32 : ((frac + 0x1000) >> 13) + 32;   // round(128 m) - 96
+    const int j = 1023 - (hi >> 20) - (big ? 1 : 0);           // -k
+    const int idx = big ? ((frac + 0x800) >> 12) - 128 : ((frac + 0x400) >> 11) + 128;   // round(512 m) - 384
     const double m = __hiloint2double(frac | (big ? 0x3fe00000 : 0x3ff00000), lo);
     const double2 tb = __ldg(reinterpret_cast<const double2*>(kLogTab) + idx);
+    const double base = __ldg(kLogExpTab + min(max(j, 0), 63)) + tb.y;
     const double t = fma(m, tb.x, -1.0);
-    double q = kLog1pC[5];
+    double q = fma(t, -2.0 / 5, kNeg2Log1pC[3]);
 #pragma unroll
-    for (int i = 4; i >= 0; --i) q = fma(q, t, kLog1pC[i]);
-    const double l1p = fma(t * t, q, t);
-    const double dk = (double)k;
-    return fma(dk, kLn2Hi, tb.y) + fma(dk, kLn2Lo, l1p);      // dk * kLn2Hi is exact (32-bit kLn2Hi)
+    for (int i = 2; i >= 0; --i) q = fma(q, t, kNeg2Log1pC[i]);
+    return fma(t, q, base);
 }
+__device__ __forceinline__ double log_pos(double u) { return -0.5 * neg2_log_pos(u); }
 
-// sqrt(x) for x in [0, 1e6]; sqrt(0) returns ~1e-15 (x is -2 ln u with P(u == 1) = 2^-53).
-// MUFU seed (22 bits) -> one Newton step on 1/sqrt (44 bits) -> one coupled step on sqrt (88 bits before rounding)
+// sqrt(x) for x in [0, 1e6] (x is -2 ln u; sqrt(0) = 0).  MUFU seed r ~ x^-1/2 (22 bits), e = 1 - x r^2 exactly rounded,
+// sqrt x = x r (1 - e)^-1/2 = x r (1 + e/2 + 3/8 e^2) with the next term 5/16 e^3 < 1e-19.  6 FP64 instructions.
 __device__ __forceinline__ double sqrt_pos(double x) {
-    const double xc = fmax(x, 1e-30);
-    double r = (double)rsqrt_approx((float)xc);
-    r = r * fma(-0.5 * xc, r * r, 1.5);
-    const double s = xc * r;
-    return fma(0.5 * r, fma(-s, s, xc), s);
+    const double r = (double)rsqrt_approx(fmaxf((float)x, 1e-30f));
+    const double e = fma(-x, r * r, 1.0);
+    const double w = x * r;
+    const double pe = fma(e, 0.375, 0.5) * e;
+    return fma(w, pe, w);
 }
 
-// sin(2 pi u), cos(2 pi u) for u in [0, 1)
+// sin(2 pi u), cos(2 pi u) for u = b 2^-53, b a 53-bit integer: u = i/256 + f 2^-53 with i = round(256 u) and the signed
+// remainder f formed in integers (exact), {sin, cos}(2 pi i/256) from a 4 KB table, h = 2 pi f 2^-53 in [-pi/256, pi/256]:
+// sin h to h^5 (remainder 8e-18), cos h - 1 to h^6 (1e-20), then the angle-sum formulas.  13 FP64 instructions.
+__device__ __forceinline__ void sincos_2pi_bits(unsigned long long b, double& sn, double& cs) {
+    const unsigned long long t = b + (1ull << 44);
+    const int idx = (int)(t >> 45) & 255;
+    const long long f = (long long)(t & ((1ull << 45) - 1)) - (1ll << 44);
+    const double2 sc = __ldg(reinterpret_cast<const double2*>(kSinCosTab) + idx);
+    const double h = (double)f * (6.283185307179586476925 * 0x1.0p-53);
+    const double h2 = h * h;
+    const double sh = fma(h * h2, fma(h2, 1.0 / 120, -1.0 / 6), h);
+    const double cm1 = h2 * fma(h2, fma(h2, -1.0 / 720, 1.0 / 24), -0.5);
+    sn = fma(sc.x, cm1, fma(sc.y, sh, sc.x));
+    cs = fma(sc.y, cm1, fma(-sc.x, sh, sc.y));
+}
+// the same for a double u in [0, 1) that is a multiple of 2^-53 (self-test entry)
 __device__ __forceinline__ void sincos_2pi(double u, double& sn, double& cs) {
-    const double t = 4.0 * u;
-    const int q = __double2int_rn(t);                  // quarter turns, 0..4
-    const double x = (t - (double)q) * 1.5707963267948966;   // in [-pi/4, pi/4]
-    const double x2 = x * x;
-    double ps = kSinC[6];
-#pragma unroll
-    for (int i = 5; i >= 0; --i) ps = fma(ps, x2, kSinC[i]);
-    double pc = kCosC[7];
-#pragma unroll
-    for (int i = 6; i >= 0; --i) pc = fma(pc, x2, kCosC[i]);
-    const double s0 = fma(x * x2, ps, x), c0 = fma(x2, pc, 1.0);
-    const bool swap = q & 1;
-    const double a = swap ? c0 : s0, b = swap ? s0 : c0;   // q=0: (s,c)  1: (c,-s)  2: (-s,-c)  3: (-c,s)
-    sn = (q & 2) ? -a : a;
-    cs = ((q + 1) & 2) ? -b : b;
+    sincos_2pi_bits((unsigned long long)(u * 0x1.0p53), sn, cs);
 }
 
 // exp(x) for x <= 700 (arguments here are <= 0 up to rounding); exp(x < -708) = 0, exp(-inf) = 0.
@@ -127,13 +130,12 @@ __device__ __forceinline__ double exp_fast(double x) {
     return (x >= -708.0) ? scaled : 0.0;                       // also x = -inf / NaN garbage -> 0
 }
 
-// two independent N(0,1) variates from one Philox block (Box-Muller, all FP64)
+// two independent N(0,1) variates from one Philox block (Box-Muller, all FP64):
+// sqrt(-2 ln u1) {cos, sin}(2 pi u2), u1 = (top 53 bits of (x, y) + 1) 2^-53 in (0, 1], u2 = (top 53 bits of (z, w)) 2^-53
 __device__ __forceinline__ void normal_pair(uint4 r, double& z0, double& z1) {
-    const double u1 = u01_open_low(r.x, r.y);
-    const double u2 = u01_half_open(r.z, r.w);
-    const double rad = sqrt_pos(-2.0 * log_pos(u1));
+    const double rad = sqrt_pos(neg2_log_pos(u01_open_low(r.x, r.y)));
     double s, c;
-    sincos_2pi(u2, s, c);
+    sincos_2pi_bits((((unsigned long long)r.z << 32) | r.w) >> 11, s, c);
     z0 = rad * c;
     z1 = rad * s;
 }
@@ -228,6 +230,34 @@ __device__ __forceinline__ void sym_expm(double (&X)[A * (A + 1) / 2], double (&
     const double scale = __hiloint2double((1023 - s) << 20, 0);
 #pragma unroll
     for (int k = 0; k < AA; ++k) X[k] *= scale;
+    if constexpr (A == 2) {
+        // two surfaces (every model of the reference's examples/paper_1.5025058): closed form instead of four products.
+        // X = m I + Y, Y = [[h, b], [b, -h]], Y^2 = q I with q = h^2 + b^2:  exp X = e^m (cosh(sqrt q) I + sinh(sqrt q)/sqrt q Y),
+        // both even series in sqrt q, cut after q^6 (|X| < 1/3 after scaling: the same degree-12 truncation as T12, all terms
+        // positive).  35 FP64 instructions instead of 66.
+        const double hd = 0.5 * X[2];
+        const double m = fma(0.5, X[0], hd), h = fma(0.5, X[0], -hd);
+        const double q = fma(h, h, X[1] * X[1]);
+        double ch = 1.0 / 479001600, sh = 1.0 / 6227020800.0;
+        ch = fma(ch, q, 1.0 / 3628800);  sh = fma(sh, q, 1.0 / 39916800);
+        ch = fma(ch, q, 1.0 / 40320);    sh = fma(sh, q, 1.0 / 362880);
+        ch = fma(ch, q, 1.0 / 720);      sh = fma(sh, q, 1.0 / 5040);
+        ch = fma(ch, q, 1.0 / 24);       sh = fma(sh, q, 1.0 / 120);
+        ch = fma(ch, q, 0.5);            sh = fma(sh, q, 1.0 / 6);
+        ch = fma(ch, q, 1.0);            sh = fma(sh, q, 1.0);
+        const double em = exp_fast(m);
+        const double es = em * sh, ec = em * ch;
+        M[0] = fma(es, h, ec);
+        M[1] = es * X[1];
+        M[2] = fma(-es, h, ec);
+        for (int r = 0; r < s; ++r) {
+            double W2[AA];
+            sym_mul<A>(M, M, W2);
+#pragma unroll
+            for (int k = 0; k < AA; ++k) M[k] = W2[k];
+        }
+        return;
+    }
     double X2[AA], X3[AA], W[AA], Y0[AA], Bm[AA];
     sym_mul<A>(X, X, X2);
     sym_mul<A>(X, X2, X3);

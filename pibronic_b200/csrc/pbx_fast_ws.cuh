@@ -34,11 +34,8 @@
 #ifndef PBX_WS_PROD_WGS
 #define PBX_WS_PROD_WGS 2    // producer warpgroups: 1 = two samples per producer thread, 2 = one
 #endif
-#ifndef PBX_WS_REG_PROD
-#define PBX_WS_REG_PROD (PBX_WS_PROD_WGS == 1 ? 56 : 32)
-#endif
-#ifndef PBX_WS_REG_CONS
-#define PBX_WS_REG_CONS 224
+#ifndef PBX_WS_CTAS
+#define PBX_WS_CTAS 0        // CTAs per SM; 0 = chosen per shape (ws_ctas)
 #endif
 #ifndef PBX_WS_PARK_NS
 #define PBX_WS_PARK_NS 400   // sleep of a waiting producer between two polls of its "empty" barrier, ns
@@ -54,6 +51,30 @@ constexpr int WS_PROD = 128 * PBX_WS_PROD_WGS, WS_CONS = 256, WS_THREADS = WS_PR
 constexpr int WS_SPT = WS_CONS / WS_PROD;   // samples per producer thread
 constexpr int WS_GROUPS = 4;                // barrier groups: 64 consumers (2 warps) and the producer warps feeding them
 constexpr int WS_GROUP_PROD = WS_PROD / WS_GROUPS;   // producer threads per group
+
+// Register budget per shape.  The 64 K registers of an SM are split between the CTAs resident on it; inside a CTA the
+// producer warpgroups hand registers to the consumer warpgroups (setmaxnreg).  A = 2 needs < 96 registers per consumer
+// thread: two CTAs per SM (16 consumer warps) hide the latency of its short dependent chains.
+template <int A, int N, int AR>
+constexpr int ws_ctas() { return PBX_WS_CTAS ? PBX_WS_CTAS : (A <= 2 ? 2 : 1); }
+template <int A, int N, int AR>
+constexpr int ws_reg_prod() {
+#ifdef PBX_WS_REG_PROD
+    return PBX_WS_REG_PROD;
+#else
+    return PBX_WS_PROD_WGS == 1 ? 56 : 32;
+#endif
+}
+template <int A, int N, int AR>
+constexpr int ws_reg_cons() {
+#ifdef PBX_WS_REG_CONS
+    return PBX_WS_REG_CONS;
+#else
+    // what the producers give up goes to the consumers, in the allocation unit of 8 registers
+    return ((65536 / ws_ctas<A, N, AR>() - WS_PROD * ws_reg_prod<A, N, AR>()) / WS_CONS) / 8 * 8 > 224
+               ? 224 : ((65536 / ws_ctas<A, N, AR>() - WS_PROD * ws_reg_prod<A, N, AR>()) / WS_CONS) / 8 * 8;
+#endif
+}
 
 template <int N>
 constexpr size_t ws_smem_bytes() {
@@ -96,7 +117,7 @@ __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 template <int A, int N, int AR, bool PM, bool SHARE, bool MTAU = false>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+__global__ void __launch_bounds__(WS_THREADS, (ws_ctas<A, N, AR>()))
 pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch L) {
     constexpr int NV = PM ? 3 : 1;
     constexpr int H = (N + 1) / 2;
@@ -132,7 +153,7 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
 
     if (tid < WS_PROD) {
         // ------------------------------------------------------------------ producer
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PBX_WS_REG_PROD));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(ws_reg_prod<A, N, AR>()));
         const int g = tid / WS_GROUP_PROD, t = tid - g * WS_GROUP_PROD;
         if (g >= n_groups || cta_first + 64 * g >= L.n_samples) return;
         int col[WS_SPT];
@@ -171,7 +192,7 @@ pbx_fast_ws_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLau
     }
 
     // ---------------------------------------------------------------------- consumer
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(PBX_WS_REG_CONS));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(ws_reg_cons<A, N, AR>()));
     const int c = tid - WS_PROD, g = c >> 6;
     if (g >= n_groups || cta_first + 64 * g >= L.n_samples) return;
     long long x = cta_first + c;
@@ -276,9 +297,10 @@ cudaError_t launch_ws_one(const FastTables<A, N, AR>& T, const FastLaunch& L_in,
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long groups = (L.n_samples + 63) / 64;
-    L.ws_full_ctas = (groups / WS_GROUPS) / sms * sms;                      // one CTA per SM: whole waves
+    const long long slots = (long long)sms * ws_ctas<A, N, AR>();            // CTAs resident at a time: one wave
+    L.ws_full_ctas = (groups / WS_GROUPS) / slots * slots;                  // whole waves
     const long long rest = groups - WS_GROUPS * L.ws_full_ctas;
-    L.ws_tail_groups = (int)std::min<long long>(WS_GROUPS, std::max<long long>(1, (rest + sms - 1) / sms));
+    L.ws_tail_groups = (int)std::min<long long>(WS_GROUPS, std::max<long long>(1, (rest + slots - 1) / slots));
     const long long blocks = L.ws_full_ctas + (rest + L.ws_tail_groups - 1) / L.ws_tail_groups;
     constexpr size_t smem = ws_smem_bytes<N>();
     auto kernel = pbx_fast_ws_kernel<A, N, AR, PM, SHARE, MTAU>;
