@@ -65,16 +65,21 @@ constexpr int ws_reg_prod() {
     return PBX_WS_PROD_WGS == 1 ? 56 : 32;
 #endif
 }
+// registers per thread the CTA is launched with (what __launch_bounds__(WS_THREADS, ctas) makes ptxas use): its pool
+template <int A, int N, int AR>
+constexpr int ws_reg_launch() { return 65536 / (WS_THREADS * ws_ctas<A, N, AR>()) / 8 * 8; }
 template <int A, int N, int AR>
 constexpr int ws_reg_cons() {
 #ifdef PBX_WS_REG_CONS
     return PBX_WS_REG_CONS;
 #else
-    // what the producers give up goes to the consumers, in the allocation unit of 8 registers
-    return ((65536 / ws_ctas<A, N, AR>() - WS_PROD * ws_reg_prod<A, N, AR>()) / WS_CONS) / 8 * 8 > 224
-               ? 224 : ((65536 / ws_ctas<A, N, AR>() - WS_PROD * ws_reg_prod<A, N, AR>()) / WS_CONS) / 8 * 8;
+    // what the producers give up goes to the consumers, in the allocation unit of 8 registers; never more than the pool
+    // of the CTA holds (setmaxnreg.inc would wait for ever)
+    return (WS_THREADS * ws_reg_launch<A, N, AR>() - WS_PROD * ws_reg_prod<A, N, AR>()) / WS_CONS / 8 * 8;
 #endif
 }
+static_assert(WS_PROD * ws_reg_prod<4, 6, 4>() + WS_CONS * ws_reg_cons<4, 6, 4>() <= WS_THREADS * ws_reg_launch<4, 6, 4>(), "register pool");
+static_assert(WS_PROD * ws_reg_prod<2, 2, 2>() + WS_CONS * ws_reg_cons<2, 2, 2>() <= WS_THREADS * ws_reg_launch<2, 2, 2>(), "register pool");
 
 template <int N>
 constexpr size_t ws_smem_bytes() {
