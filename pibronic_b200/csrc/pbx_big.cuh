@@ -23,6 +23,7 @@
 // Reference: /root/reference/pibronic/pimc/pimc.py:326-334, 613-631 (sampler), 1087-1129 (O), 1076-1084 (S),
 // 1132-1136 (rho), 1139-1187 (V, M), 1194-1209 (chain), 1413-1449 (order of operations in block_compute_pm).
 #pragma once
+#include <atomic>
 #include <type_traits>
 
 #include "pbx_dmma.cuh"
@@ -199,8 +200,16 @@ __device__ __forceinline__ void big_frag_store(double* __restrict__ buf, const B
         }
 }
 
-template <int AT, bool PM, int MODE>
-__global__ void __launch_bounds__(BIG_WARPS * 32, 1)
+// CTAs per SM the kernel is compiled for: up to 8 surfaces every matrix is a single 8 x 8 tile and 128 registers hold
+// the fragments, so two CTAs (16 warps, four per scheduler) share an SM when their shared memory fits as well -- the
+// per-bead stage of the small shapes is latency bound (short dependent DMMA chains); above, one CTA with 255 registers
+#ifndef PBX_BIG_CTAS_SMALL
+#define PBX_BIG_CTAS_SMALL 2
+#endif
+__host__ __device__ constexpr int big_min_ctas(int AT) { return AT <= 8 ? PBX_BIG_CTAS_SMALL : 1; }
+
+template <int AT, bool PM, int MODE, int CTAS = 1>
+__global__ void __launch_bounds__(BIG_WARPS * 32, CTAS)
 pbx_big_kernel(const BigParams Q) {
     extern __shared__ __align__(16) double sm[];
     using Sh = MidShape<AT>;
@@ -754,12 +763,33 @@ inline size_t big_smem_bytes(int A, bool pm, int N, int Ar, int tab_doubles, int
 
 template <int AT>
 cudaError_t launch_big_at(const BigParams& Q, bool pm, int mode, size_t smem, int sms, cudaStream_t st) {
-    const long long ctas = std::min<long long>((Q.n_samples + 0) > 0 ? Q.n_samples : 1, sms);
 #define PBX_BIG_GO(PM_, MODE_)                                                                                       \
     {                                                                                                                \
-        auto k = pbx_big_kernel<AT, PM_, MODE_>;                                                                     \
+        /* the 128-register build when two of its CTAs fit an SM (shared memory decides: N, A_rho), else the */      \
+        /* one-CTA build; persistent grid: as many CTAs as are resident at a time */                                 \
+        if constexpr (big_min_ctas(AT) > 1) {                                                                        \
+            auto k2 = pbx_big_kernel<AT, PM_, MODE_, big_min_ctas(AT)>;                                              \
+            cudaError_t e2 = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+            if (e2 != cudaSuccess) return e2;                                                                        \
+            static std::atomic<unsigned long long> memo{0};      /* (smem << 8 | CTAs per SM) of the last query */   \
+            const unsigned long long seen = memo.load(std::memory_order_relaxed);                                    \
+            int per_sm = (int)(seen & 0xff);                                                                         \
+            if ((seen >> 8) != (unsigned long long)smem || per_sm == 0) {                                            \
+                e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, BIG_WARPS * 32, smem);               \
+                if (e2 != cudaSuccess) return e2;                                                                    \
+                per_sm = std::max(1, std::min(per_sm, 255));                                                         \
+                memo.store(((unsigned long long)smem << 8) | (unsigned)per_sm, std::memory_order_relaxed);           \
+            }                                                                                                        \
+            if (per_sm >= 2) {                                                                                       \
+                const long long ctas = std::min<long long>(Q.n_samples > 0 ? Q.n_samples : 1, (long long)sms * per_sm); \
+                k2<<<(unsigned)ctas, BIG_WARPS * 32, smem, st>>>(Q);                                                 \
+                return cudaGetLastError();                                                                           \
+            }                                                                                                        \
+        }                                                                                                            \
+        auto k = pbx_big_kernel<AT, PM_, MODE_, 1>;                                                                  \
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
         if (e != cudaSuccess) return e;                                                                              \
+        const long long ctas = std::min<long long>(Q.n_samples > 0 ? Q.n_samples : 1, sms);                          \
         k<<<(unsigned)ctas, BIG_WARPS * 32, smem, st>>>(Q);                                                          \
         return cudaGetLastError();                                                                                   \
     }
