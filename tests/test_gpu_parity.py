@@ -278,6 +278,30 @@ def test_minimum_and_odd_bead_counts(cuda, P, variant):
     plan.close()
 
 
+@pytest.mark.parametrize("variant", ["default", "generic", "fused_dmma"])
+@pytest.mark.parametrize("name", ["c1_2x2", "quad_3x4", "c2_4x6"])
+def test_strong_coupling_takes_the_squaring_path(cuda, name, variant):
+    """few beads and a large inter-surface coupling: ||tau V|| is far above 1/3, so exp(-tau V) runs its squaring loop
+    (after the closed form for two surfaces, after the four-product polynomial otherwise)"""
+    import copy
+    from conftest import GoldenCase
+    from oracle import pimc_oracle as orc
+    case = GoldenCase(name)
+    case.P = 4
+    case.vib = copy.deepcopy(case.vib)
+    A = case.vib["E"].shape[0]
+    case.vib["E"] = case.vib["E"] + 0.15 * (1.0 - np.eye(A))
+    tau_v = orc.beta_of(case.T) / case.P * 0.15 * (A - 1)
+    assert tau_v > 1.0
+    plan = case.plan(_cabi.FLAG_PM | VARIANTS[variant])
+    tab = orc.precompute(case.vib, case.rho, case.P, case.T)
+    n = 96
+    out = plan.sample_eval_host(5, 0, n)
+    R, _ = drawn_coords(cuda, plan, 5, 0, n)
+    assert rel_err(out, oracle_eval(tab, R)) < RTOL
+    plan.close()
+
+
 def test_non_pm_plan_fills_two_rows(cuda, case):
     plan = case.plan(flags=_cabi.QUIRK_RHO_TRUNC)
     out = np.full((2, len(case.R)), np.nan)
