@@ -41,6 +41,9 @@ run("c1 A=2 N=2 P=12", c1, synthetic.diagonal_of(c1), 12, 10_000_000)
 run("c3 A=2 N=2 P=128", c3, synthetic.diagonal_of(c3), 128, 100_000)
 run("c3 A=2 N=2 P=128", c3, synthetic.diagonal_of(c3), 128, 1_000_000)
 run("c3 A=2 N=2 P=128 non-PM", c3, synthetic.diagonal_of(c3), 128, 1_000_000, flags=0)
+run("c3 one-role kernel", c3, synthetic.diagonal_of(c3), 128, 1_000_000, flags=_cabi.FLAG_PM | _cabi.FLAG_NO_WARPSPEC)
+run("c3 one-role kernel", c3, synthetic.diagonal_of(c3), 128, 100_000, flags=_cabi.FLAG_PM | _cabi.FLAG_NO_WARPSPEC)
+run("c1 one-role kernel", c1, synthetic.diagonal_of(c1), 12, 10_000, flags=_cabi.FLAG_PM | _cabi.FLAG_NO_WARPSPEC)
 m323 = synthetic.coupled_model(3, 3, (0.02, 0.04), (0.1, 0.2), seed=5, linear=0.05, quadratic=0.02)
 run("A=3 N=3 P=64", m323, synthetic.diagonal_of(m323), 64, 1_000_000)
 c2 = synthetic.model_c2()
