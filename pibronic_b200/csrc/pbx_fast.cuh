@@ -439,9 +439,22 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
     };   // process
 
     if constexpr (MODE == MODE_REDO) {
-        // no block-wide barrier in this kernel: every thread scans its own stride of the result array
-        for (long long x = (long long)blockIdx.x * nt + tid; x < L.n_samples; x += (long long)gridDim.x * nt)
-            if (isnan(L.out4[x])) process(x, true);
+        // no block-wide barrier in this kernel: every thread scans its own stride of the result array, eight loads in flight
+        // (the scan of 1e6 results is latency bound: 16 us with one load at a time)
+        const long long stride = (long long)gridDim.x * nt;
+        for (long long x0 = (long long)blockIdx.x * nt + tid; x0 < L.n_samples; x0 += 8 * stride) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (x0 + k * stride < L.n_samples) ? __ldcg(L.out4 + x0 + k * stride) : 0.0;
+            unsigned flagged = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) flagged |= isnan(v[k]) ? (1u << k) : 0u;
+            while (flagged) {
+                const int k = __ffs(flagged) - 1;
+                flagged &= flagged - 1;
+                process(x0 + k * stride, true);
+            }
+        }
     } else {
         const long long x = (long long)blockIdx.x * nt + tid;
         const bool live = x < L.n_samples;
