@@ -60,7 +60,6 @@ struct DeviceGuard {
 };
 
 constexpr size_t kScratchTarget = (size_t)4 << 30;  // aim for <= 4 GiB of intermediates per chunk (the sampler kernel of the large-A path needs ~1e4 samples to fill the GPU)
-constexpr long long kFastCoordChunk = 4 * 148 * 2 * 128;  // samples per transposed-coordinate chunk: 4 full waves of CTAs
 
 // ---- per-block sums ------------------------------------------------------------------------
 // grid (estimator blocks, split): CTA (b, s) reduces slice s of block b with a fixed-order tree; the last CTA of a
@@ -710,22 +709,12 @@ int pbx_eval_coords_dev(pbx_plan* p, const double* R, int64_t n, double* out4, v
     DeviceGuard guard(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const HostTables& H = p->H;
-    if (p->fast) {
-        const long long chunk = std::min<long long>(kFastCoordChunk, n);
-        const long long ld = (chunk + 31) / 32 * 32, np = (long long)H.N * H.P;
-        int rc = ensure(&p->scratch, &p->scratch_bytes, (size_t)ld * np * sizeof(double));
-        if (rc != PBX_OK) return rc;
-        for (long long off = 0; off < n; off += chunk) {
-            const long long m = std::min<long long>(chunk, n - off);
-            dim3 grid((unsigned)((np + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
-            pbx_transpose_kernel<<<grid, block, 0, st>>>(R + (size_t)off * np, (double*)p->scratch, m, np, ld);
-            PBX_CUDA(cudaGetLastError());
-            FastLaunch L{};
-            L.samp = p->D.samp; L.coords_t = (const double*)p->scratch; L.ld = ld; L.n_samples = m;
-            L.out4 = out4 + off; L.out_ld = n;
-            PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_COORDS, p->pm, p->jacobi, p->H.rho_shares_vib, p->mtau, st));
-            p->launches += 2;
-        }
+    if (p->fast) {      // one launch, the caller's R read in place
+        FastLaunch L{};
+        L.samp = p->D.samp; L.coords = R; L.n_samples = n;
+        L.out4 = out4; L.out_ld = n;
+        PBX_CUDA(p->fast->launch(p->fast_tables.data(), L, MODE_COORDS, p->pm, p->jacobi, p->H.rho_shares_vib, p->mtau, st));
+        p->launches += 1;
         return PBX_OK;
     }
     if (p->big) return launch_big(p, R, 0, 0, n, out4, n, nullptr, 0, st);      // reads the caller's R in place

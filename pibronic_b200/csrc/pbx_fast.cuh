@@ -74,8 +74,7 @@ struct FastTables {
 
 struct FastLaunch {
     const double* samp;      // [P][N][3] recurrence table (global)
-    const double* coords_t;  // MODE_COORDS: transposed coordinates [N][P][ld]
-    long long ld;            // leading dimension (samples) of coords_t
+    const double* coords;    // MODE_COORDS: the caller's coordinates R[x][N][P], read in place
     unsigned long long seed;
     long long first_sample;  // global index of sample 0 of this launch (Philox counter)
     long long n_samples;
@@ -353,10 +352,12 @@ pbx_fast_kernel(const __grid_constant__ FastTables<A, N, AR> T, const FastLaunch
                 }
             }
         } else {
-            const double* src = L.coords_t + (size_t)(j == P ? 0 : j) * L.ld + x;
+            // the caller's R[x][n][p] read in place: the lanes of a warp are N P doubles apart, but a lane's 32-byte sector
+            // serves four consecutive beads from L1 (DRAM traffic 1.2x the array; a transposed copy cost 3x and a pass)
+            const double* src = L.coords + (size_t)x * N * P + (j == P ? 0 : j);
             double v[N];
 #pragma unroll
-            for (int n = 0; n < N; ++n) v[n] = __ldg(src + (size_t)n * P * L.ld);   // all loads in flight together
+            for (int n = 0; n < N; ++n) v[n] = __ldg(src + (size_t)n * P);   // all loads in flight together
 #pragma unroll
             for (int n = 0; n < N; ++n) dst[n * nt] = v[n];
         }

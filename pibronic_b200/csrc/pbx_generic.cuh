@@ -310,23 +310,4 @@ pbx_chain_kernel(DevTables T, const double* __restrict__ m_mat, const double* __
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// layout helpers
-// ---------------------------------------------------------------------------------------------
-// in[rows][cols] -> out[cols][ld_out] (first `rows` columns of each output row)
-__global__ void pbx_transpose_kernel(const double* __restrict__ in, double* __restrict__ out, long long rows,
-                                     long long cols, long long ld_out) {
-    __shared__ double tile[32][33];
-    const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
-    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
-        const long long r = r0 + dy, c = c0 + threadIdx.x;
-        if (r < rows && c < cols) tile[dy][threadIdx.x] = in[r * cols + c];
-    }
-    __syncthreads();
-    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
-        const long long c = c0 + dy, r = r0 + threadIdx.x;
-        if (r < rows && c < cols) out[c * ld_out + r] = tile[threadIdx.x][dy];
-    }
-}
-
 }  // namespace pbx
