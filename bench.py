@@ -21,6 +21,9 @@ roofline     : FP64 units.  achieved = algorithmic flop/sample (SURVEY.md sectio
 other_configs: every other BASELINE.json configuration at its stated size (c1 X=1e4, c3 P=128, c4 X=1e7 over the GPUs
                of the run, c5 = c2 sampled from another rho), each with ms, samples*beads/s and its roofline fraction
                under the same flop rule.
+coords_mode  : pbx_eval_coords on 1e6 device-resident c2 samples per GPU (the entry the parity tests and the
+               *_from_raw_samples block drivers use): the only configuration with inputs in HBM -- achieved GB/s of the
+               co-ordinate array against MEASURED_PEAKS.json's copy bandwidth next to the FP64 fraction (no sampler term).
 strong_scaling: c2 at a FIXED total of 1e6 samples and c4 at a fixed total of 1e7, split over the N GPUs.
 cpu_baseline / --impl reference: the UNMODIFIED reference's block_compute_pm (staged into baseline/_ref by
                baseline/stage_reference.py; kind "reference") on a bounded sample, one process per host core with
@@ -57,12 +60,13 @@ WORKLOAD = (f"c2: synthetic A={A} N={N} P={P} lin+quad coupling, T={T_KELVIN:.0f
             f"X={X_PER_GPU:.0e} samples/GPU/step in blocks of {BLOCK_SIZE}")
 
 
-def algorithmic_flops_per_sample(A, N, P, Ar):
+def algorithmic_flops_per_sample(A, N, P, Ar, sampler=True):
     """SURVEY.md section 8(d) strict count (transcendental = 1 flop).  F_x is the sequential ring
-    recurrence actually used (1 mul + 2 fma per coordinate), not the reference's dense PxP product.
+    recurrence actually used (1 mul + 2 fma per coordinate), not the reference's dense PxP product
+    (sampler=False: co-ordinates supplied by the caller, no F_x).
     The ONE flop rule of this repository: every roofline fraction (bench, DESIGN.md, profiles/) uses it."""
     nn, aa = N * (N + 1) // 2, A * (A + 1) // 2
-    F_x = 5 * N * P
+    F_x = 5 * N * P if sampler else 0
     F_O = N * P * (20 * A + 8 * Ar)
     F_V = P * (nn + 2 * nn * aa + 2 * N * A * (A - 1) // 2 + aa)
     F_eig = 9 * A ** 3 * P
@@ -317,6 +321,48 @@ def other_configs(run, device):
     return lines
 
 
+def coords_mode(run, plan, x=1_000_000, reps=5):
+    """the other entry of the path: pbx_eval_coords on device-resident co-ordinates R[x][N][P] (what the parity tests and
+    the block drivers *_from_raw_samples use).  The only configuration with HBM-resident inputs: 8 N P + 32 bytes per sample."""
+    torch = run.torch
+    R = torch.empty((x, plan.N, plan.P), dtype=torch.float64, device="cuda")
+    out = torch.empty((4, x), dtype=torch.float64, device="cuda")
+    plan.sample_coords(11, run.rank * x, x, R)
+    plan.eval_coords(R[:4096], out[:, :4096].contiguous())
+    run.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total = 0.0
+    for k in range(reps):
+        run.flush.fill_(float(k))
+        e0.record()
+        plan.eval_coords(R, out)
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    (ms,) = run.max_over_ranks([total / reps])
+    fused = torch.empty_like(out)
+    plan.sample_eval(11, run.rank * x, x, fused)
+    same = bool(torch.equal(fused, out))
+    assert same, "co-ordinate mode and the fused sampler disagree on the same Philox counters"
+    flops = algorithmic_flops_per_sample(plan.A, plan.N, plan.P, plan.Ar, sampler=False)
+    rate = x * run.world / (ms * 1e-3)
+    hbm_peak = None
+    try:
+        with open(join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            hbm_peak = float(json.load(fh)["hbm_gbs"])
+    except (OSError, KeyError, ValueError):
+        pass
+    gbs = (8 * plan.N * plan.P + 32) * rate / run.world / 1e9
+    del R
+    return {"call": "pbx_eval_coords_dev on device-resident R[x][N][P] (c2 model), read in place by the register-resident kernel",
+            "samples_per_gpu": x, "n_gpus": run.world, "ms": ms, "samples_beads_per_s": rate * plan.P,
+            "flop_per_sample": flops, "tflops": flops * rate / 1e12, "frac_of_fp64_peak": flops * rate / 1e12 / (run.peak * run.world),
+            "algorithmic_bytes_per_sample": 8 * plan.N * plan.P + 32, "hbm_gbs_per_gpu": gbs, "hbm_peak_gbs": hbm_peak,
+            "frac_of_hbm_peak": (gbs / hbm_peak) if hbm_peak else None,
+            "bit_identical_to_fused_sampler": same,
+            "note": "FP64 bound, not HBM bound: the estimator alone (no sampler warps competing for the FP64 units)"}
+
+
 def shard_check(run, plan):
     """the union of the ranks' shards is bit-identical to one GPU evaluating the whole index range"""
     torch, dist = run.torch, run.dist
@@ -470,6 +516,7 @@ def run_b200(args, rank, local_rank, world):
     x_rank = C2_STRONG_TOTAL // world
     strong_ms, _ = run.time_fused(plan, x_rank, 20, seed=31, block_size=BLOCK_SIZE)
     others = other_configs(run, local_rank)
+    coords = coords_mode(run, plan)
 
     if rank == 0:
         flops = algorithmic_flops_per_sample(A, N, P, A)
@@ -527,6 +574,7 @@ def run_b200(args, rank, local_rank, world):
             "gpu_launches": int(gpu_launches),
             "clocks": clock_info,
             "other_configs": others,
+            "coords_mode": coords,
             "strong_scaling": {
                 "c2": {"samples_total": x_rank * world, "n_gpus": world, "ms": strong_ms,
                        "samples_beads_per_s": x_rank * world * P / (strong_ms * 1e-3),
