@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -58,6 +59,50 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync on a private stream):
+// a cudaFree costs ~0.3 ms (it synchronises the device and unmaps), and a plan owns up to eight buffers -- a temperature
+// x bead sweep creates and destroys a plan per point.  The pool keeps up to 512 MB of freed blocks for re-use.
+// Callers free only after the work that used the block has completed (plan_destroy and ensure synchronise first).
+struct PoolState {
+    cudaStream_t stream = nullptr;
+    bool ready = false;
+};
+static PoolState g_pool[64];
+static std::mutex g_pool_mutex;
+
+static cudaError_t pool_stream(cudaStream_t* out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    PoolState& st = g_pool[dev];
+    if (!st.ready) {
+        cudaMemPool_t pool;
+        if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
+        unsigned long long keep = 512ull << 20;
+        if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        st.ready = true;
+    }
+    *out = st.stream;
+    return cudaSuccess;
+}
+
+static cudaError_t dev_alloc(void** ptr, size_t bytes) {
+    cudaStream_t st;
+    cudaError_t e = pool_stream(&st);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(ptr, bytes, st)) != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);       // the block is valid on every stream from here on
+}
+
+static void dev_free(void* ptr) {
+    if (!ptr) return;
+    cudaStream_t st;
+    if (pool_stream(&st) != cudaSuccess || cudaFreeAsync(ptr, st) != cudaSuccess) { cudaGetLastError(); cudaFree(ptr); }
+}
 
 constexpr size_t kScratchTarget = (size_t)4 << 30;  // aim for <= 4 GiB of intermediates per chunk (the sampler kernel of the large-A path needs ~1e4 samples to fill the GPU)
 
@@ -255,8 +300,8 @@ namespace {
 
 int ensure(void** buf, size_t* have, size_t need) {
     if (need <= *have) return PBX_OK;
-    if (*buf) { PBX_CUDA(cudaDeviceSynchronize()); PBX_CUDA(cudaFree(*buf)); *buf = nullptr; *have = 0; }
-    PBX_CUDA(cudaMalloc(buf, need));
+    if (*buf) { PBX_CUDA(cudaDeviceSynchronize()); dev_free(*buf); *buf = nullptr; *have = 0; }
+    PBX_CUDA(dev_alloc(buf, need));
     *have = need;
     return PBX_OK;
 }
@@ -271,7 +316,7 @@ int upload_tables(pbx_plan* p) {
     const size_t o_dv = push(H.d_vib), o_dr = push(H.d_rho_eval), o_hc = push(hc), o_cs = push(cs), o_lp = push(H.logpref),
                  o_lpr = push(H.logpref_rho), o_wc = push(H.wcum), o_e = push(H.e_off), o_l = push(H.l_off),
                  o_q = push(H.q_pack), o_s = push(H.samp);
-    PBX_CUDA(cudaMalloc((void**)&p->dev_tables, flat.size() * sizeof(double)));
+    PBX_CUDA(dev_alloc((void**)&p->dev_tables, flat.size() * sizeof(double)));
     PBX_CUDA(cudaMemcpy(p->dev_tables, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
     DevTables& D = p->D;
     D.A = H.A; D.Ar = H.Ar; D.N = H.N; D.P = H.P; D.AA = H.AA; D.NN = H.NN; D.n_rho_eval = H.n_rho_eval;
@@ -318,12 +363,12 @@ int upload_dmma_tables(pbx_plan* p) {
     // two tables: the coefficients as they are (blocked kernels: they also return V) and multiplied by -tau (fused kernel:
     // its tensor-core contraction yields X = -tau V directly)
     double* dq = nullptr;
-    PBX_CUDA(cudaMalloc((void**)&dq, 2 * q.size() * sizeof(double)));
+    PBX_CUDA(dev_alloc((void**)&dq, 2 * q.size() * sizeof(double)));
     p->dmma_tables = dq;
     PBX_CUDA(cudaMemcpy(dq, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
     for (double& v : q) v *= -H.tau[0];
     PBX_CUDA(cudaMemcpy(dq + q.size(), q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
-    PBX_CUDA(cudaMalloc((void**)&p->dev_int_tables, ints.size() * sizeof(int)));
+    PBX_CUDA(dev_alloc((void**)&p->dev_int_tables, ints.size() * sizeof(int)));
     PBX_CUDA(cudaMemcpy(p->dev_int_tables, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice));
     p->D.q_dmma = dq; p->D.feat = p->dev_int_tables; p->D.tri_ij = p->dev_int_tables + 4 * KS;
     p->D.KS = KS; p->D.NT = NT;
@@ -356,7 +401,7 @@ int upload_big_tables(pbx_plan* p) {
     PBX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
     PBX_CUDA(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
     if (p->big_smem > (size_t)max_smem) { p->big = nullptr; return PBX_OK; }   // falls back to the blocked kernels
-    PBX_CUDA(cudaMalloc((void**)&p->big_tab, flat.size() * sizeof(double)));
+    PBX_CUDA(dev_alloc((void**)&p->big_tab, flat.size() * sizeof(double)));
     PBX_CUDA(cudaMemcpy(p->big_tab, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
     B.tab = p->big_tab;
     B.Ar = Ar; B.N = N; B.P = H.P; B.n_rho_eval = H.n_rho_eval; B.KS = p->D.KS; B.neg_tau = -H.tau[0];
@@ -567,14 +612,14 @@ int pbx_plan_destroy(pbx_plan* p) {
     if (p->device < 0) { delete p; return PBX_OK; }
     DeviceGuard guard(p->device);
     cudaDeviceSynchronize();
-    if (p->dev_tables) cudaFree(p->dev_tables);
-    if (p->dev_int_tables) cudaFree(p->dev_int_tables);
-    if (p->dmma_tables) cudaFree(p->dmma_tables);
-    if (p->big_tab) cudaFree(p->big_tab);
-    if (p->scratch) cudaFree(p->scratch);
-    if (p->io) cudaFree(p->io);
-    if (p->stat_partials) cudaFree(p->stat_partials);
-    if (p->sums_scratch) cudaFree(p->sums_scratch);
+    dev_free(p->dev_tables);
+    dev_free(p->dev_int_tables);
+    dev_free(p->dmma_tables);
+    dev_free(p->big_tab);
+    dev_free(p->scratch);
+    dev_free(p->io);
+    dev_free(p->stat_partials);
+    dev_free(p->sums_scratch);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
     return PBX_OK;
@@ -911,7 +956,7 @@ int pbx_stats_dev(pbx_plan* p, const double* out4, int64_t n, double* stats_host
     if (!p->pm) return fail(PBX_ERR_ARG, "statistics need a PBX_FLAG_PM plan (g+ and g-)");
     PBX_NEED_DEVICE(p);
     DeviceGuard guard(p->device);
-    if (!p->stat_partials) PBX_CUDA(cudaMalloc((void**)&p->stat_partials, kStatGrid * 4 * sizeof(double)));
+    if (!p->stat_partials) PBX_CUDA(dev_alloc((void**)&p->stat_partials, kStatGrid * 4 * sizeof(double)));
     p->launches += 2;
     return stats_core(out4, n, p->H.beta, p->H.delta_beta, p->stat_partials, stats_host, (cudaStream_t)stream);
 }
@@ -927,9 +972,9 @@ int pbx_stats_arrays_dev(const double* out4, int64_t n, double beta, double delt
     if (device < 0 || device >= ndev) return fail(PBX_ERR_ARG, "device index out of range");
     DeviceGuard guard(device);
     double* partials = nullptr;
-    PBX_CUDA(cudaMalloc((void**)&partials, kStatGrid * 4 * sizeof(double)));
-    const int rc = stats_core(out4, n, beta, delta_beta, partials, stats_host, (cudaStream_t)stream);
-    cudaFree(partials);
+    PBX_CUDA(dev_alloc((void**)&partials, kStatGrid * 4 * sizeof(double)));
+    const int rc = stats_core(out4, n, beta, delta_beta, partials, stats_host, (cudaStream_t)stream);   // returns after its D2H copy
+    dev_free(partials);
     return rc;
 }
 
@@ -942,10 +987,10 @@ int pbx_stats_arrays_host(const double* out4_host, int64_t ld_host, int64_t n, d
     if (device < 0 || device >= ndev) return fail(PBX_ERR_ARG, "device index out of range");
     DeviceGuard guard(device);
     double* dev = nullptr;
-    PBX_CUDA(cudaMalloc((void**)&dev, (size_t)4 * n * sizeof(double)));
+    PBX_CUDA(dev_alloc((void**)&dev, (size_t)4 * n * sizeof(double)));
     cudaError_t e = cudaMemcpy2D(dev, n * sizeof(double), out4_host, ld_host * sizeof(double), n * sizeof(double), 4, cudaMemcpyHostToDevice);
     int rc = e == cudaSuccess ? pbx_stats_arrays_dev(dev, n, beta, delta_beta, device, stats_host, nullptr) : cuda_fail(e, "cudaMemcpy2D");
-    cudaFree(dev);
+    dev_free(dev);
     return rc;
 }
 
