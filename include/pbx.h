@@ -154,7 +154,8 @@ int pbx_sample_eval_dev(pbx_plan *plan, uint64_t seed, int64_t first_sample, int
 int pbx_sample_eval_host(pbx_plan *plan, uint64_t seed, int64_t first_sample, int64_t n_samples,
                          double *out4_host, int64_t ld_host, int64_t block_size, double *sums_host);
 
-/* Estimator on caller supplied bead coordinates R[n_samples][N][P] (the reference's qTensor[:,0]). */
+/* Estimator on caller supplied bead coordinates R[n_samples][N][P] (the reference's qTensor[:,0]).
+ * R_dev is read in place (no staging copy, no scratch for the register-resident and tensor-core kernels). */
 int pbx_eval_coords_dev(pbx_plan *plan, const double *R_dev, int64_t n_samples, double *out4_dev,
                         void *stream);
 int pbx_eval_coords_host(pbx_plan *plan, const double *R_host, int64_t n_samples, double *out4_host,
