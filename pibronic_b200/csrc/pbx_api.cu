@@ -283,6 +283,7 @@ struct pbx_plan {
     BigParams B{};
     double* big_tab = nullptr;
     size_t big_smem = 0;
+    int big_warps = BIG_WARPS;     // warps per CTA of the fused tensor-core kernel (fewer when eight do not fit the SM)
     int sms = 148;
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -396,10 +397,15 @@ int upload_big_tables(pbx_plan* p) {
     B.o_drho = (int)flat.size();
     flat.insert(flat.end(), H.d_rho.begin(), H.d_rho.end());
     B.tab_doubles = (int)flat.size();
-    p->big_smem = big_smem_bytes(A, p->pm, N, Ar, B.tab_doubles, p->D.KS);
     int max_smem = 0;
     PBX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
     PBX_CUDA(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
+    // eight warps (two per scheduler) per CTA; shapes whose per-warp regions do not fit eight times (A > 12 with many
+    // modes) run four, one per scheduler
+    for (p->big_warps = BIG_WARPS; p->big_warps >= 4; p->big_warps /= 2) {
+        p->big_smem = big_smem_bytes(A, p->pm, N, Ar, B.tab_doubles, p->D.KS, p->big_warps);
+        if (p->big_smem <= (size_t)max_smem) break;
+    }
     if (p->big_smem > (size_t)max_smem) { p->big = nullptr; return PBX_OK; }   // falls back to the blocked kernels
     PBX_CUDA(dev_alloc((void**)&p->big_tab, flat.size() * sizeof(double)));
     PBX_CUDA(cudaMemcpy(p->big_tab, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -417,7 +423,7 @@ int launch_big(pbx_plan* p, const double* R, uint64_t seed, long long first, lon
     BigParams B = p->B;
     B.R = R; B.seed = seed; B.first_sample = first; B.n_samples = n; B.out4 = out4; B.out_ld = out_ld;
     B.mirror = mirror; B.mirror_ld = mirror_ld;
-    PBX_CUDA(p->big(B, p->pm, R ? BIG_COORDS : BIG_SAMPLE, p->big_smem, p->sms, st));
+    PBX_CUDA(p->big(B, p->pm, R ? BIG_COORDS : BIG_SAMPLE, p->big_smem, p->sms, p->big_warps, st));
     p->launches += 1;
     return PBX_OK;
 }

@@ -242,8 +242,10 @@ pbx_big_kernel(const BigParams Q) {
     double* ring = sm + big_even(Q.tab_doubles) + 4 * Q.KS;
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + (size_t)BIG_STAGES * stage_doubles);
     uint64_t* bar_empty = bar_full + BIG_STAGES;
-    const long long nwarps = (long long)gridDim.x * BIG_WARPS;
-    const long long iters = (Q.n_samples - blockIdx.x + (long long)gridDim.x * BIG_WARPS - 1) / ((long long)gridDim.x * BIG_WARPS);
+    // warps per CTA: BIG_WARPS, or fewer when the per-warp regions of a large shape do not fit the SM eight times
+    const int cta_warps = (int)(blockDim.x >> 5);
+    const long long nwarps = (long long)gridDim.x * cta_warps;
+    const long long iters = (Q.n_samples - blockIdx.x + nwarps - 1) / nwarps;
     const int n_chunks = Q.KS / BIG_CH;
     // the CTA consumes the ring in one sequence of chunks, the same in every warp; slot and phase advance incrementally
     // (no divisions on the critical path: thread 0, the producer, must not fall behind the other warps)
@@ -260,7 +262,7 @@ pbx_big_kernel(const BigParams Q) {
                           q_src + (size_t)k0 * NT * 32 + q * (stage_doubles / BIG_COPY_SPLIT), bytes / BIG_COPY_SPLIT, &bar_full[slot]);
     };
     if (threadIdx.x == 0) {
-        for (int st = 0; st < BIG_STAGES; ++st) { big_mbar_init(&bar_full[st], 1); big_mbar_init(&bar_empty[st], BIG_WARPS); }
+        for (int st = 0; st < BIG_STAGES; ++st) { big_mbar_init(&bar_full[st], 1); big_mbar_init(&bar_empty[st], cta_warps); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async;\n" ::: "memory");
     }
@@ -303,14 +305,14 @@ pbx_big_kernel(const BigParams Q) {
                 aci[mt][nt][e] = (i < AT && j < AT) ? sym(i, j) : -1;
             }
     // weights of the lane's packed entries in the Frobenius norm (diagonal 1, off-diagonal 2, padding 0) as bit masks
-    unsigned fro_valid = 0u, fro_diag = 0u;
+    unsigned long long fro_valid = 0ull, fro_diag = 0ull;     // two bits per tile: 34 bits at 16 surfaces (17 tiles)
 #pragma unroll
     for (int j = 0; j < NT; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int ij = __ldg(Q.tri_ij + 8 * j + 2 * c + e);
-            if (ij >= 0) fro_valid |= 1u << (2 * j + e);
-            if (ij >= 0 && (ij >> 16) == (ij & 0xffff)) fro_diag |= 1u << (2 * j + e);
+            if (ij >= 0) fro_valid |= 1ull << (2 * j + e);
+            if (ij >= 0 && (ij >> 16) == (ij & 0xffff)) fro_diag |= 1ull << (2 * j + e);
         }
     // variant of the stacked-chain rows this lane holds
     int vrow[MTS];
@@ -569,8 +571,8 @@ pbx_big_kernel(const BigParams Q) {
                 for (int j = 0; j < NT; ++j) {
                     const double x0 = acc[m][j][0], x1 = acc[m][j][1];          // the table carries the factor -tau
                     *reinterpret_cast<double2*>(Xs + (8 * m + g) * XSTR + 8 * j + 2 * c) = make_double2(x0, x1);
-                    const double w0 = ((fro_valid >> (2 * j)) & 1u) ? (((fro_diag >> (2 * j)) & 1u) ? 1.0 : 2.0) : 0.0;
-                    const double w1 = ((fro_valid >> (2 * j + 1)) & 1u) ? (((fro_diag >> (2 * j + 1)) & 1u) ? 1.0 : 2.0) : 0.0;
+                    const double w0 = ((fro_valid >> (2 * j)) & 1ull) ? (((fro_diag >> (2 * j)) & 1ull) ? 1.0 : 2.0) : 0.0;
+                    const double w1 = ((fro_valid >> (2 * j + 1)) & 1ull) ? (((fro_diag >> (2 * j + 1)) & 1ull) ? 1.0 : 2.0) : 0.0;
                     fro = fma(w0 * x0, x0, fma(w1 * x1, x1, fro));
                 }
                 fro += __shfl_xor_sync(0xffffffffu, fro, 1);
@@ -757,12 +759,12 @@ pbx_big_kernel(const BigParams Q) {
 }
 
 // shared memory of one CTA, bytes
-inline size_t big_smem_bytes(int A, bool pm, int N, int Ar, int tab_doubles, int KS) {
-    return ((size_t)big_cta_doubles(tab_doubles, KS, (A * (A + 1) / 2 + 7) / 8) + (size_t)BIG_WARPS * big_layout(A, pm ? 3 : 1, N, Ar).total) * sizeof(double);
+inline size_t big_smem_bytes(int A, bool pm, int N, int Ar, int tab_doubles, int KS, int warps = BIG_WARPS) {
+    return ((size_t)big_cta_doubles(tab_doubles, KS, (A * (A + 1) / 2 + 7) / 8) + (size_t)warps * big_layout(A, pm ? 3 : 1, N, Ar).total) * sizeof(double);
 }
 
 template <int AT>
-cudaError_t launch_big_at(const BigParams& Q, bool pm, int mode, size_t smem, int sms, cudaStream_t st) {
+cudaError_t launch_big_at(const BigParams& Q, bool pm, int mode, size_t smem, int sms, int warps, cudaStream_t st) {
 #define PBX_BIG_GO(PM_, MODE_)                                                                                       \
     {                                                                                                                \
         /* the 128-register build when two of its CTAs fit an SM (shared memory decides: N, A_rho), else the */      \
@@ -774,15 +776,15 @@ cudaError_t launch_big_at(const BigParams& Q, bool pm, int mode, size_t smem, in
             static std::atomic<unsigned long long> memo{0};      /* (smem << 8 | CTAs per SM) of the last query */   \
             const unsigned long long seen = memo.load(std::memory_order_relaxed);                                    \
             int per_sm = (int)(seen & 0xff);                                                                         \
-            if ((seen >> 8) != (unsigned long long)smem || per_sm == 0) {                                            \
-                e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, BIG_WARPS * 32, smem);               \
+            if ((seen >> 8) != ((unsigned long long)smem << 4 | (unsigned)warps) || per_sm == 0) {                                            \
+                e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, warps * 32, smem);               \
                 if (e2 != cudaSuccess) return e2;                                                                    \
                 per_sm = std::max(1, std::min(per_sm, 255));                                                         \
-                memo.store(((unsigned long long)smem << 8) | (unsigned)per_sm, std::memory_order_relaxed);           \
+                memo.store((((unsigned long long)smem << 4 | (unsigned)warps) << 8) | (unsigned)per_sm, std::memory_order_relaxed);           \
             }                                                                                                        \
             if (per_sm >= 2) {                                                                                       \
                 const long long ctas = std::min<long long>(Q.n_samples > 0 ? Q.n_samples : 1, (long long)sms * per_sm); \
-                k2<<<(unsigned)ctas, BIG_WARPS * 32, smem, st>>>(Q);                                                 \
+                k2<<<(unsigned)ctas, warps * 32, smem, st>>>(Q);                                                 \
                 return cudaGetLastError();                                                                           \
             }                                                                                                        \
         }                                                                                                            \
@@ -790,7 +792,7 @@ cudaError_t launch_big_at(const BigParams& Q, bool pm, int mode, size_t smem, in
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
         if (e != cudaSuccess) return e;                                                                              \
         const long long ctas = std::min<long long>(Q.n_samples > 0 ? Q.n_samples : 1, sms);                          \
-        k<<<(unsigned)ctas, BIG_WARPS * 32, smem, st>>>(Q);                                                          \
+        k<<<(unsigned)ctas, warps * 32, smem, st>>>(Q);                                                          \
         return cudaGetLastError();                                                                                   \
     }
     if (pm) { if (mode == BIG_SAMPLE) PBX_BIG_GO(true, BIG_SAMPLE) else PBX_BIG_GO(true, BIG_COORDS) }
@@ -799,7 +801,7 @@ cudaError_t launch_big_at(const BigParams& Q, bool pm, int mode, size_t smem, in
 }
 
 // defined in pbx_big_inst.cu, one translation unit per A
-typedef cudaError_t (*BigLauncher)(const BigParams&, bool, int, size_t, int, cudaStream_t);
+typedef cudaError_t (*BigLauncher)(const BigParams&, bool, int, size_t, int, int, cudaStream_t);
 BigLauncher find_big_kernel(int A);
 
 }  // namespace pbx

@@ -496,6 +496,39 @@ def test_c4_shape_runs_on_the_fused_tensor_core_kernel(cuda):
     plan.close()
 
 
+@pytest.mark.parametrize("shape", [(16, 24, 20), (14, 20, 33), (13, 5, 16), (16, 3, 7)])
+def test_more_than_twelve_surfaces_run_fused(cuda, shape):
+    """13..16 surfaces (two 8 x 8 tiles per matrix row, the widest the kernel is built for): the fused tensor-core kernel
+    with eight warps per CTA, or four when the per-warp regions of the shape do not fit the SM eight times (16 x 24);
+    against the oracle on the sampler's co-ordinates, the co-ordinate entry point and the blocked kernels; more samples
+    than one pass of the resident warps"""
+    from oracle import pimc_oracle as orc
+    from pibronic_b200 import constants, synthetic
+    from pibronic_b200.model_io import VMK
+    A, N, P = shape
+    model = synthetic.coupled_model(A, N, (0.1, 0.39), (14.0, 14.8), seed=A * 100 + N)
+    rho = synthetic.diagonal_of(model)
+    args = (model[VMK.E], model[VMK.w], model[VMK.G1], model[VMK.G2], rho[VMK.E], rho[VMK.w], rho[VMK.G1],
+            P, constants.beta(300.0), constants.delta_beta)
+    plan = _cabi.Plan(*args, flags=_cabi.FLAG_PM, device=0)
+    assert plan.kernel_path == _cabi.PATH_FUSED_DMMA
+    vib_d = dict(A=A, N=N, E=model[VMK.E], w=model[VMK.w], L=model[VMK.G1], Q=model[VMK.G2])
+    rho_d = dict(A=A, N=N, E=rho[VMK.E], w=rho[VMK.w], L=rho[VMK.G1])
+    tab = orc.precompute(vib_d, rho_d, P, 300.0)
+    n = 40
+    out = plan.sample_eval_host(3, 17, n)
+    R, _ = drawn_coords(cuda, plan, 3, 17, n)
+    assert rel_err(out, oracle_eval(tab, R)) < RTOL
+    assert np.array_equal(out, plan.eval_coords_host(R))
+    many = plan.sample_eval_host(3, 0, 148 * 8 + 57)
+    assert np.array_equal(many[:, 17:17 + n], out)
+    blocked = _cabi.Plan(*args, flags=_cabi.FLAG_PM | _cabi.FLAG_NO_FUSED_DMMA, device=0)
+    assert blocked.kernel_path == _cabi.PATH_BLOCKED
+    assert rel_err(blocked.sample_eval_host(3, 17, n), out) < RTOL
+    blocked.close()
+    plan.close()
+
+
 def test_fused_tensor_core_kernel_many_passes_and_splits(cuda):
     """more samples than resident warps (148 SMs x 8): several passes per warp, a partly filled last pass, results
     independent of how the index range is cut, non-PM variant fills two rows"""
