@@ -529,6 +529,19 @@ def test_more_than_twelve_surfaces_run_fused(cuda, shape):
     plan.close()
 
 
+def test_random_shapes_against_the_oracle(cuda):
+    """tools/fuzz_shapes.py: 40 random (A <= 16, N, A_rho, P, T, PM) models, four kernel selections each (default, one-role +
+    Jacobi, tensor-core preferred, generic forced) against the oracle on the sampler's co-ordinates, fused == co-ordinate entry"""
+    import importlib.util
+    from os.path import dirname, join
+    spec = importlib.util.spec_from_file_location("fuzz_shapes", join(dirname(dirname(__file__)), "tools", "fuzz_shapes.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    worst, failures, seen = fuzz.run(40, 2026, verbose=False)
+    assert not failures, "\n".join(failures)
+    assert worst < RTOL and {"tensor", "register", "blocked"} <= set(seen)
+
+
 def test_fused_tensor_core_kernel_many_passes_and_splits(cuda):
     """more samples than resident warps (148 SMs x 8): several passes per warp, a partly filled last pass, results
     independent of how the index range is cut, non-PM variant fills two rows"""

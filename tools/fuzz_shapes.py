@@ -1,0 +1,108 @@
+"""Randomised shape sweep on the GPU box: every kernel family against the oracle on the device sampler's co-ordinates.
+
+    python tools/fuzz_shapes.py [cases] [seed]
+
+Shapes: 1..16 surfaces, 1..26 modes, 3..70 beads, sampling models with fewer / equal / more surfaces than the system,
+PM and non-PM, strong and weak coupling (few beads -> squarings of exp(-tau V)).  Checks per case: default path vs oracle,
+fused launch == sampler + co-ordinate entry (bit for bit), the forced generic kernels vs oracle.
+"""
+import sys
+from os.path import abspath, dirname, join
+
+ROOT = dirname(dirname(abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from oracle import pimc_oracle as orc
+from pibronic_b200 import _cabi, constants, synthetic
+from pibronic_b200.model_io import VMK
+
+RTOL = 1e-10
+PATHS = {_cabi.PATH_REGISTER: "register", _cabi.PATH_FUSED_DMMA: "tensor", _cabi.PATH_BLOCKED: "blocked", _cabi.PATH_GENERIC: "generic"}
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+def run(cases, seed, verbose=True):
+    """returns (worst relative error, list of failing case lines, kernel paths seen)"""
+    rng = np.random.default_rng(seed)
+    worst, seen, failures = 0.0, {}, []
+    for k in range(cases):
+        listed = None
+        if rng.random() < 0.4:                      # a shape with a register-resident kernel (csrc/shapes.def)
+            listed = [(2, 2, 2), (2, 2, 4), (2, 2, 8), (2, 3, 2), (3, 3, 3), (3, 4, 3), (3, 6, 3), (4, 4, 4), (4, 6, 4)][int(rng.integers(0, 9))]
+        A = listed[0] if listed else int(rng.integers(1, 17))
+        N = listed[1] if listed else int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 24, 26]))
+        if A * N > 200:
+            N = max(1, 200 // A)
+        P = int(rng.choice([3, 4, 5, 7, 8, 12, 16, 17, 31, 32, 33, 64, 70]))
+        pm = bool(rng.integers(0, 2))
+        T = float(rng.choice([150.0, 300.0, 1000.0]))
+        model = synthetic.coupled_model(A, N, (0.05, 0.4), (5.0, 5.8), seed=int(rng.integers(1 << 30)),
+                                        linear=float(rng.choice([0.05, 0.2])), quadratic=float(rng.choice([0.0, 0.05, 0.15])),
+                                        mixing=float(rng.choice([0.0, 0.25])))
+        rho = synthetic.diagonal_of(model)
+        Ar = A
+        mode = int(rng.integers(0, 4))
+        if listed and listed[2] == A:
+            mode = 0
+        elif listed:                                # the listed wider mixture
+            mode, Ar = 3, listed[2]
+            reps = -(-Ar // A)
+            rho = {VMK.N: N, VMK.A: Ar, VMK.w: rho[VMK.w], VMK.E: np.tile(rho[VMK.E], reps)[:Ar] + 0.01 * np.arange(Ar),
+                   VMK.G1: np.tile(rho[VMK.G1], (1, reps))[:, :Ar] * (1 + 0.05 * np.arange(Ar))}
+        if mode == 1 and A > 1:                     # fewer sampling surfaces than the system
+            Ar = int(rng.integers(1, A))
+            rho = {VMK.N: N, VMK.A: Ar, VMK.w: rho[VMK.w], VMK.E: rho[VMK.E][:Ar].copy(), VMK.G1: rho[VMK.G1][:, :Ar].copy()}
+        elif mode == 2 and A < 12:                  # more: a widened mixture
+            Ar = int(min(32, A + rng.integers(1, 5)))
+            reps = -(-Ar // A)
+            rho = {VMK.N: N, VMK.A: Ar, VMK.w: rho[VMK.w], VMK.E: np.tile(rho[VMK.E], reps)[:Ar] + 0.01 * np.arange(Ar),
+                   VMK.G1: np.tile(rho[VMK.G1], (1, reps))[:, :Ar] * (1 + 0.05 * np.arange(Ar))}
+        args = (model[VMK.E], model[VMK.w], model[VMK.G1], model[VMK.G2], rho[VMK.E], rho[VMK.w], rho[VMK.G1], P,
+                constants.beta(T), constants.delta_beta)
+        vib_d = dict(A=A, N=N, E=model[VMK.E], w=model[VMK.w], L=model[VMK.G1], Q=model[VMK.G2])
+        rho_d = dict(A=Ar, N=N, E=rho[VMK.E], w=rho[VMK.w], L=rho[VMK.G1])
+        tab = orc.precompute(vib_d, rho_d, P, T)
+        rows = 4 if pm else 2
+        n = 20
+        line = f"[{k:3d}] A={A:2d} N={N:2d} Ar={Ar:2d} P={P:2d} pm={int(pm)} T={T:6.0f}"
+        for flags in (0, _cabi.FLAG_NO_WARPSPEC | _cabi.FLAG_EIG_JACOBI, _cabi.FLAG_PREFER_DMMA, _cabi.FLAG_FORCE_GENERIC):
+            try:
+                plan = _cabi.Plan(*args, flags=(_cabi.FLAG_PM if pm else 0) | flags, device=0)
+            except _cabi.PbxError as err:
+                line += f"  plan: {err}"
+                continue
+            R = torch.empty((n, N, P), dtype=torch.float64, device="cuda")
+            plan.sample_coords(5, 1000 + k, n, R)
+            Rh = R.cpu().numpy()
+            want = np.stack(orc.estimate_block(tab, Rh, pm=pm, faithful=False))[:rows]
+            got = plan.eval_coords_host(Rh, out4=np.full((rows, n), np.nan))
+            fused = plan.sample_eval_host(5, 1000 + k, n, out4=np.full((rows, n), np.nan))
+            err = rel(got, want)
+            same = bool(np.array_equal(got, fused))
+            worst = max(worst, err)
+            path = PATHS[plan.kernel_path]
+            seen[path] = seen.get(path, 0) + 1
+            line += f"  {path}: {err:.1e}{'' if same else ' FUSED!=COORDS'}"
+            if not (err < RTOL) or not same:
+                line += "  <-- FAIL"
+            plan.close()
+        if "FAIL" in line or "plan:" in line:
+            failures.append(line)
+        if verbose:
+            print(line, flush=True)
+    return worst, failures, seen
+
+
+def main():
+    worst, failures, seen = run(int(sys.argv[1]) if len(sys.argv) > 1 else 120, int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    print("worst relative error", worst, "paths", seen, "failures", len(failures))
+
+
+if __name__ == "__main__":
+    main()
