@@ -311,8 +311,10 @@ int upload_tables(pbx_plan* p) {
     const HostTables& H = p->H;
     std::vector<double> flat;
     auto push = [&](const std::vector<double>& v) { size_t off = flat.size(); flat.insert(flat.end(), v.begin(), v.end()); return off; };
-    std::vector<double> hc(H.coth.size()), cs(H.csch);
-    for (size_t i = 0; i < hc.size(); ++i) hc[i] = -0.5 * H.coth[i];
+    // harmonic exponent in half-angle form, -1/4 [tanh(x/2) (q + q')^2 + coth(x/2) (q - q')^2]: the reference's
+    // coth (q^2 + q'^2) - 2 csch q q' cancels digits for tau*omega << 1 (DESIGN.md section 2 iii); every kernel uses this form
+    std::vector<double> hc(H.tanh_half.size()), cs(H.coth_half.size());
+    for (size_t i = 0; i < hc.size(); ++i) { hc[i] = -0.25 * H.tanh_half[i]; cs[i] = -0.25 * H.coth_half[i]; }
     const size_t o_drs = push(H.d_rho);
     const size_t o_dv = push(H.d_vib), o_dr = push(H.d_rho_eval), o_hc = push(hc), o_cs = push(cs), o_lp = push(H.logpref),
                  o_lpr = push(H.logpref_rho), o_wc = push(H.wcum), o_e = push(H.e_off), o_l = push(H.l_off),

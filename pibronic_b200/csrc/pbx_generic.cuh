@@ -19,7 +19,7 @@ struct DevTables {
     double neg_tau;
     const double *d_vib, *d_rho;     // [A][N], [Ar][N]: shifts in the harmonic exponents
     const double *d_rho_samp;        // [Ar][N]: shift of the drawn mixture component (== d_rho unless PBX_QUIRK_RHO_DOUBLE_SHIFT)
-    const double *hc, *cs;           // [4][N]  (-0.5 coth, csch)
+    const double *hc, *cs;           // [4][N]  (-1/4 tanh(x/2), -1/4 coth(x/2)), x = tau omega
     const double *lpref, *lpref_rho; // [3][A], [Ar]
     const double *wcum;              // [Ar]
     const double *e_off, *l_off, *q_pack;  // [AA], [N][AA], [NN][AA]
@@ -199,7 +199,8 @@ pbx_bead_kernel(DevTables T, const double* __restrict__ R, long long n_samples, 
         double acc = is_rho ? T.lpref_rho[a] : T.lpref[v * A + a];
         for (int n = 0; n < N; ++n) {
             const double q = Rc[n] - d[n], qn = Rn[n] - d[n];
-            acc = fma(T.hc[v * N + n], fma(q, q, qn * qn), fma(T.cs[v * N + n], q * qn, acc));
+            const double sp = q + qn, sm = Rc[n] - Rn[n];
+            acc = fma(T.hc[v * N + n], sp * sp, fma(T.cs[v * N + n], sm * sm, acc));
         }
         if (is_rho) lr[a] = (a < T.n_rho_eval) ? acc : -INFINITY;
         else lv[it] = acc;

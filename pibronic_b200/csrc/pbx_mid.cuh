@@ -262,12 +262,14 @@ pbx_mid_bead_kernel(DevTables T, const double* __restrict__ R, long long n_sampl
         for (int jj = 0; jj < MID_IB; ++jj) acc[jj] = start;
         for (int n = 0; n < N; ++n) {
             const double dn = d[n], hc = T.hc[v * N + n], cs = T.cs[v * N + n];
-            double q[MID_IB + 1];
+            double r[MID_IB + 1];
 #pragma unroll
-            for (int jj = 0; jj <= MID_IB; ++jj) q[jj] = Rt[n * MID_RS + jj] - dn;
+            for (int jj = 0; jj <= MID_IB; ++jj) r[jj] = Rt[n * MID_RS + jj];
 #pragma unroll
-            for (int jj = 0; jj < MID_IB; ++jj)
-                acc[jj] = fma(hc, fma(q[jj], q[jj], q[jj + 1] * q[jj + 1]), fma(cs, q[jj] * q[jj + 1], acc[jj]));
+            for (int jj = 0; jj < MID_IB; ++jj) {
+                const double sp = (r[jj] - dn) + (r[jj + 1] - dn), sm = r[jj] - r[jj + 1];
+                acc[jj] = fma(hc, sp * sp, fma(cs, sm * sm, acc[jj]));
+            }
         }
         const bool dead = is_rho && a >= T.n_rho_eval;
 #pragma unroll

@@ -3,8 +3,9 @@
     python tools/fuzz_shapes.py [cases] [seed]
 
 Shapes: 1..16 surfaces, 1..26 modes, 3..70 beads, sampling models with fewer / equal / more surfaces than the system,
-PM and non-PM, strong and weak coupling (few beads -> squarings of exp(-tau V)).  Checks per case: default path vs oracle,
-fused launch == sampler + co-ordinate entry (bit for bit), the forced generic kernels vs oracle.
+PM and non-PM, strong and weak coupling (few beads -> squarings of exp(-tau V)); `extreme`: 128..500 beads, 31..40 modes,
+40..3000 K.  Checks per case and kernel selection: result vs oracle (vs the 80-bit evaluation of tests/golden/extended_precision.py
+where the oracle itself is ill-conditioned), fused launch == sampler + co-ordinate entry (bit for bit).
 """
 import sys
 from os.path import abspath, dirname, join
@@ -15,6 +16,9 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
+sys.path.insert(0, join(ROOT, "tests", "golden"))
+
+import extended_precision
 from oracle import pimc_oracle as orc
 from pibronic_b200 import _cabi, constants, synthetic
 from pibronic_b200.model_io import VMK
@@ -27,7 +31,7 @@ def rel(a, b):
     return float(np.max(np.abs(a - b) / np.abs(b)))
 
 
-def run(cases, seed, verbose=True):
+def run(cases, seed, verbose=True, extreme=False):
     """returns (worst relative error, list of failing case lines, kernel paths seen)"""
     rng = np.random.default_rng(seed)
     worst, seen, failures = 0.0, {}, []
@@ -42,6 +46,14 @@ def run(cases, seed, verbose=True):
         P = int(rng.choice([3, 4, 5, 7, 8, 12, 16, 17, 31, 32, 33, 64, 70]))
         pm = bool(rng.integers(0, 2))
         T = float(rng.choice([150.0, 300.0, 1000.0]))
+        if extreme:                                 # long ring polymers, the 32-mode limit of the on-chip sampler, cold and hot
+            P = int(rng.choice([3, 128, 255, 256, 500]))
+            T = float(rng.choice([40.0, 300.0, 3000.0]))
+            if not listed:
+                N = int(rng.choice([1, 31, 32, 33, 40]))
+                A = int(rng.choice([1, 2, 5, 8, 9, 12, 16]))
+                if A * N > 400:
+                    A = max(1, 400 // N)
         model = synthetic.coupled_model(A, N, (0.05, 0.4), (5.0, 5.8), seed=int(rng.integers(1 << 30)),
                                         linear=float(rng.choice([0.05, 0.2])), quadratic=float(rng.choice([0.0, 0.05, 0.15])),
                                         mixing=float(rng.choice([0.0, 0.25])))
@@ -80,10 +92,21 @@ def run(cases, seed, verbose=True):
             R = torch.empty((n, N, P), dtype=torch.float64, device="cuda")
             plan.sample_coords(5, 1000 + k, n, R)
             Rh = R.cpu().numpy()
-            want = np.stack(orc.estimate_block(tab, Rh, pm=pm, faithful=False))[:rows]
+            with np.errstate(all="ignore"):
+                want = np.stack(orc.estimate_block(tab, Rh, pm=pm, faithful=False))[:rows]
+            if not (np.all(np.isfinite(want)) and np.all(want[0] > 0)):      # the reference's formulas under/overflow here
+                line += "  (oracle not finite: skipped)"
+                plan.close()
+                break
             got = plan.eval_coords_host(Rh, out4=np.full((rows, n), np.nan))
             fused = plan.sample_eval_host(5, 1000 + k, n, out4=np.full((rows, n), np.nan))
             err = rel(got, want)
+            if not err < RTOL:
+                # tau*omega << 1 with hundreds of beads: the reference's own float64 formulas (which the oracle restates)
+                # cancel digits (DESIGN.md section 2 iii) -- the yardstick is then the 80-bit evaluation of the same formulas
+                exact = np.asarray(extended_precision.evaluate(vib_d, rho_d, P, T, Rh, rho_trunc=False)[:rows], dtype=np.float64)
+                line += f"  [oracle off by {rel(want, exact):.1e} from 80-bit]"
+                err = rel(got, exact)
             same = bool(np.array_equal(got, fused))
             worst = max(worst, err)
             path = PATHS[plan.kernel_path]
@@ -100,7 +123,8 @@ def run(cases, seed, verbose=True):
 
 
 def main():
-    worst, failures, seen = run(int(sys.argv[1]) if len(sys.argv) > 1 else 120, int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    worst, failures, seen = run(int(sys.argv[1]) if len(sys.argv) > 1 else 120, int(sys.argv[2]) if len(sys.argv) > 2 else 1,
+                                extreme="extreme" in sys.argv[3:])
     print("worst relative error", worst, "paths", seen, "failures", len(failures))
 
 
