@@ -641,6 +641,32 @@ def test_device_statistics_match_the_reference(cuda):
         assert np.isclose(basic[key], want_basic[key], rtol=1e-11, atol=1e-300), key
 
 
+@pytest.mark.parametrize("n", [2, 3, 31, 33, 591, 592, 593, 4097, 100_001])
+def test_device_statistics_ragged_sizes(cuda, n):
+    """sample counts around the warp, the grid (592 CTAs) and block boundaries of the statistics kernels, with a padded
+    row stride, against the numpy restatement of the reference's jackknife; block sums with a ragged last block"""
+    from oracle import pimc_oracle as orc
+    from oracle import stats_oracle
+    rng = np.random.default_rng(n)
+    store = np.full((4, n + 5), np.nan)
+    out = store[:, :n]
+    out[0] = rng.uniform(0.5, 1.5, n)
+    out[1] = out[0] * rng.uniform(2.0, 3.0, n)
+    out[2] = out[1] * (1 + 1e-4 * rng.normal(size=n))
+    out[3] = out[1] * (1 - 1e-4 * rng.normal(size=n))
+    T = 300.0
+    got = _cabi.stats_arrays_host(out, orc.beta_of(T), orc.DELTA_BETA)
+    want = stats_oracle.basic_jackknife_analysis(T, *out)
+    for key, value in want.items():
+        if n == 2 and key.endswith("error") and key.startswith("jk"):
+            continue                                  # two samples: the spread of two leave-one-out values is all rounding
+        tol = 1e-5 if key.startswith("jk_") else 1e-9
+        assert np.isclose(got[key], value, rtol=tol, atol=1e-12 * max(1.0, abs(value))), f"{key}: {got[key]} vs {value}"
+    with cuda.cuda.device(0):
+        dev = cuda.from_numpy(np.ascontiguousarray(out)).cuda()
+        assert _cabi.stats_arrays_dev(dev, orc.beta_of(T), orc.DELTA_BETA) == got
+
+
 def test_device_statistics_at_scale_match_oracle(cuda):
     """1e6 samples straight from the device-resident results of the last run vs the numpy restatement"""
     from oracle import stats_oracle
