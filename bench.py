@@ -311,6 +311,8 @@ def other_configs(run, device):
     c3 = synthetic.coupled_model(2, 2, (0.02, 0.04), (0.1, 0.2), seed=3, linear=0.05, quadratic=0.0)
     go("c3", c3, synthetic.diagonal_of(c3), 128, 100_000 * world, 10,
        "paper_1.5025058-like 2x2 model, P=128, X=1e5 per shard (the reference's shard size)")
+    go("c3_x1e6", c3, synthetic.diagonal_of(c3), 128, 1_000_000 * world, 5,
+       "the same 2x2 model and P=128 with 1e6 samples per launch (26 waves instead of 2.6: what a GPU shard would use)")
     c4 = synthetic.model_c4()
     go("c4", c4, synthetic.diagonal_of(c4), 256, C4_TOTAL, 1,
        "A=12 N=24 P=256, X=1e7 TOTAL over the GPUs of this run (strong scaling: the stated configuration at N=8)")
