@@ -69,7 +69,7 @@ enum {
     PBX_FLAG_NO_SCALING     = 1u << 5, /* skip the per-bead S scaling (golden test of the reference)       */
     PBX_FLAG_NO_WARPSPEC    = 1u << 6, /* fused sampler+estimator on the one-role kernel instead of the        */
                                        /* producer/consumer (warp-specialised) one; same results bit for bit  */
-    PBX_FLAG_NO_FUSED_DMMA  = 1u << 7, /* 2 <= A <= 16 without a register-resident kernel: the blocked kernels   */
+    PBX_FLAG_NO_FUSED_DMMA  = 1u << 7, /* 1 <= A <= 16 without a register-resident kernel: the blocked kernels   */
                                        /* through HBM scratch instead of the fused one-launch tensor-core kernel  */
     PBX_FLAG_PREFER_DMMA    = 1u << 8, /* use the fused tensor-core kernel even where a register-resident one exists */
     PBX_QUIRK_RHO_DOUBLE_SHIFT = 1u << 9 /* reference quirk pimc.py:1293-1298 (block_compute_rhoR_from_input_samples): rho(R) is   */
@@ -81,7 +81,7 @@ enum {
     PBX_PATH_GENERIC    = 0,  /* any A: warp per (sample, bead) + warp per sample, through HBM scratch          */
     PBX_PATH_REGISTER   = 1,  /* listed small shapes: one sample per thread, everything in registers            */
     PBX_PATH_BLOCKED    = 2,  /* A <= 16: four blocked kernels through HBM scratch (round-1 large-A path)       */
-    PBX_PATH_FUSED_DMMA = 3   /* 2 <= A <= 16: one launch, one warp per sample, FP64 tensor cores, no scratch   */
+    PBX_PATH_FUSED_DMMA = 3   /* 1 <= A <= 16: one launch, one warp per sample, FP64 tensor cores, no scratch   */
 };
 
 /* coupled (vibronic) model: pibronic `coupled_model.json` arrays as loaded by ModelClass.load_model */

@@ -30,7 +30,7 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
     os.environ.get("PBX_EXTRA_NVCC_FLAGS", "").split()
 
 
-BIG_SURFACES = range(2, 17)     # keep in step with PBX_BIG_LIST in csrc/pbx_api.cu
+BIG_SURFACES = range(1, 17)     # keep in step with PBX_BIG_LIST in csrc/pbx_api.cu
 
 
 def shapes():

@@ -18,7 +18,7 @@
 using namespace pbx;
 
 namespace pbx {
-#define PBX_BIG_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#define PBX_BIG_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 #define PBX_BIG_DECL(A_) extern const BigLauncher big_launcher_##A_;
 PBX_BIG_LIST(PBX_BIG_DECL)
 #undef PBX_BIG_DECL

@@ -1,4 +1,4 @@
-// Fused large-A kernel (5 <= A <= 16 surfaces, any N, A_rho <= 32; BASELINE config c4: A=12, N=24, P=256).
+// Fused large-A kernel (1 <= A <= 16 surfaces, any N, A_rho <= 32; BASELINE config c4: A=12, N=24, P=256).
 //
 // ONE WARP PER SAMPLE, the whole estimator in one launch: nothing but the 32-byte result leaves the SM (the blocked
 // kernels of pbx_mid.cuh wrote, re-read, re-wrote and re-read M through HBM: ~1.4 MB per c4 sample).  The warp walks

@@ -2,7 +2,7 @@
 
 The one-sample-per-thread kernels (csrc/pbx_fast.cuh, pbx_fast_ws.cuh) need the number of surfaces, modes and sampling
 surfaces at compile time; ``csrc/shapes.def`` lists the shapes the library ships with.  Any other shape runs, by
-default, on the fused tensor-core kernel (csrc/pbx_big.cuh: one launch, any 2 <= A <= 16).  For SMALL shapes the
+default, on the fused tensor-core kernel (csrc/pbx_big.cuh: one launch, any 1 <= A <= 16).  For SMALL shapes the
 register-resident form is faster; ``ensure_shape(A, N, A_rho)`` compiles it on demand:
 
     nvcc -shared ... -DPBX_A=.. -DPBX_N=.. -DPBX_AR=.. -DPBX_JIT_LIBRARY csrc/pbx_fast_inst.cu -o _jit/pbx_fast_A_N_AR_<digest>.so
